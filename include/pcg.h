@@ -1,0 +1,189 @@
+/* pcg.h — C ABI of libpcg.so: the B200-native CLIP-guidance hot path (loss forward + backward to the image).
+ *
+ * This is the drop-in boundary for perceptor's one data-parallel hot path.  The reference has no FFI on this
+ * path (it is eager PyTorch); each entry point below names the reference code it replaces (paths relative to
+ * the reference repo root, perceptor v0.6.7).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`.
+ *  - the library never allocates or frees device memory; the caller sizes buffers with pcg_workspace_bytes()
+ *    and pcg_stash_bytes() and owns them.
+ *  - `stream` is a cudaStream_t passed as void*; every launch goes to it; no host synchronisation inside.
+ *  - return value: 0 = ok, negative = argument error, positive = cudaError_t.  pcg_last_error() returns a
+ *    thread-local, human-readable message for the last non-zero return.
+ *  - bf16 buffers are passed as void* (raw __nv_bfloat16 bits).
+ */
+#ifndef PCG_H_
+#define PCG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCG_ABI_VERSION 1
+
+enum { PCG_ACT_QUICKGELU = 0, PCG_ACT_GELU = 1 };
+
+/* GEMM epilogues (C = A[M,K] * B[N,K]^T, bf16 inputs, fp32 accumulation in tensor memory). */
+enum {
+    PCG_GEMM_BF16 = 0,     /* out(bf16) = acc (+ bias)                                     */
+    PCG_GEMM_BIAS_ACT = 1, /* out(bf16) = h = acc + bias ; out2(bf16) = act(h)             */
+    PCG_GEMM_RESID_F32 = 2,/* out(f32)  = aux(f32 residual) + acc + bias                   */
+    PCG_GEMM_DACT = 3,     /* out(bf16) = acc * act'(aux(bf16 pre-activation))             */
+    PCG_GEMM_F32 = 4       /* out(f32)  = acc (+ bias)                                     */
+};
+
+/* Vision-transformer shape.  Mirrors the constructor arguments of the in-tree OpenAI-CLIP VisionTransformer
+ * (perceptor/models/ruclip/model.py:72-103) that open_clip builds for perceptor/models/open_clip.py:65-72. */
+typedef struct pcg_vit_config {
+    int32_t image_size; /* R: 224 / 336                                   */
+    int32_t patch;      /* p: 32 / 16 / 14                                */
+    int32_t grid;       /* g = R / p                                      */
+    int32_t tokens;     /* T = g*g + 1                                    */
+    int32_t width;      /* D                                              */
+    int32_t layers;     /* L                                              */
+    int32_t heads;      /* D / 64 (head dim must be 64)                   */
+    int32_t mlp;        /* 4*D                                            */
+    int32_t embed;      /* E: output dim of `proj`                        */
+    int32_t kpatch;     /* 3*p*p                                          */
+    int32_t kpad;       /* kpatch rounded up to a multiple of 64          */
+    int32_t act;        /* PCG_ACT_*                                      */
+} pcg_vit_config;
+
+/* One ResidualAttentionBlock (ruclip/model.py:25-54).  w_* are bf16 [out,in] row-major (nn.Linear layout);
+ * w_*_t are their transposes [in,out] used by the dgrad GEMMs.  The 1/sqrt(64) attention scale is folded
+ * into the q rows of w_qkv / b_qkv (exact: a power of two). */
+typedef struct pcg_layer_weights {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    const void *w_qkv, *w_qkv_t; /* [3D,D], [D,3D] */
+    const void *w_out, *w_out_t; /* [D,D]          */
+    const void *w_fc, *w_fc_t;   /* [4D,D], [D,4D] */
+    const void *w_proj, *w_proj_t; /* [D,4D], [4D,D] */
+    const float *b_qkv, *b_out, *b_fc, *b_proj;
+} pcg_layer_weights;
+
+typedef struct pcg_vit_weights {
+    const void *conv1, *conv1_t;      /* bf16 [D,kpad], [kpad,D]; columns >= kpatch are zero   */
+    const float *cls, *pos;           /* [D], [T,D]                                            */
+    const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+    const float *proj;                /* fp32 [D,E]                                            */
+    const pcg_layer_weights *layers_host; /* HOST array of `layers` entries                    */
+} pcg_vit_weights;
+
+/* Resize tables (S1).  One entry per distinct (input size, method); built on the host with the reference's own
+ * fp32 arithmetic (perceptor/transforms/resize/resize_right.py:192-285) and uploaded once.
+ *   desc[id] = {taps, left_off, weight_off, inv_off, in_size, 0,0,0}   (int32 x 8)
+ *   left[left_off + o]            = first input index of output o (may be <0 or reach >= in_size: zero pad)
+ *   weight[weight_off + o*taps+t] = weight of tap t of output o
+ *   inv[inv_off + 2*i + {0,1}]    = [lo,hi) range of outputs that read input i                */
+typedef struct pcg_resize_tables {
+    const int32_t *desc;
+    const int32_t *left;
+    const float *weight;
+    const int32_t *inv;
+    int32_t n_desc;
+} pcg_resize_tables;
+
+/* Cutout rows (S0), int32 x 8 per cutout: {b, y0, x0, size_h, size_w, table_id_h, table_id_w, 0}. */
+#define PCG_CUT_STRIDE 8
+
+const char *pcg_last_error(void);
+int pcg_abi_version(void);
+int pcg_device_sm_count(void);
+
+/* ---- S0+S1+S2: cutout + antialiased resize + normalize --------------------------------------------------
+ * replaces resize(images, out_shape=image_size) + torchvision Normalize in
+ * perceptor/models/open_clip.py:109-118 (resize = perceptor/transforms/resize/resize_right.py:34-189).
+ * images f32 [B,3,H,W].  patches_bf16 (nullable) [n_cut*g*g, kpad]: row = (cutout, gy, gx),
+ * col = c*p*p + py*p + px (the flattening of conv1.weight, ruclip/model.py:85-91), cols >= 3*p*p untouched
+ * (caller zero-fills once).  out_f32 (nullable) [n_cut,3,R,R].  mean/std_inv: 3 host floats each. */
+int pcg_sampler_fwd(const float *images, int B, int H, int W, const int32_t *cuts, int n_cut,
+                    const pcg_resize_tables *tabs, int R, int patch, int kpad, const float *mean_host,
+                    const float *std_host, void *patches_bf16, float *out_f32, int max_in_w, void *stream);
+/* backward of the above: d_patches bf16 [n_cut*g*g, kpad] -> atomically accumulated into d_images f32
+ * [B,3,H,W] (caller zeroes it).  replaces autograd through resize_right.apply_weights (:288-318). */
+int pcg_sampler_bwd(const void *d_patches_bf16, const float *d_out_f32, int B, int H, int W, const int32_t *cuts,
+                    int n_cut, const pcg_resize_tables *tabs, int R, int patch, int kpad, const float *std_host,
+                    float *d_images, int max_in_w, void *stream);
+
+/* ---- tcgen05 GEMM: out[M,N] = epilogue(A[M,K] * B[N,K]^T) -------------------------------------------------
+ * replaces nn.Linear / conv1-as-GEMM forward and dgrad (ruclip/model.py:31-39,43-49,85-91).
+ * A bf16 [M,lda], B bf16 [N,ldb], K % 8 == 0, lda/ldb % 8 == 0, N % 32 == 0; out/out2/aux have row stride ldo. */
+int pcg_gemm_bf16(int mode, int act, int M, int N, int K, const void *A, int lda, const void *B, int ldb,
+                  const float *bias, const void *aux, void *out, void *out2, int ldo, void *stream);
+
+/* ---- LayerNorm (fp32 residual stream in, bf16 GEMM operand out) ------------------------------------------
+ * replaces LayerNorm.forward (ruclip/model.py:11-17), eps = 1e-5. */
+int pcg_layernorm_fwd(const float *x, const float *gamma, const float *beta, void *y_bf16, int rows, int D,
+                      void *stream);
+/* dx_io(f32) += LN'(x)^T dy ; also writes the bf16 copy of the updated dx (next dgrad GEMM operand). */
+int pcg_layernorm_bwd(const void *dy_bf16, const float *x, const float *gamma, float *dx_io, void *dx_bf16,
+                      int rows, int D, void *stream);
+
+/* ---- class token + positional embedding + ln_pre (ruclip/model.py:109-120) ------------------------------
+ * patch_out f32 [n*g*g, D] -> v f32 [n*T, D] (pre-LN, stashed) and x0 f32 [n*T, D]. */
+int pcg_embed_fwd(const float *patch_out, const float *cls, const float *pos, const float *gamma,
+                  const float *beta, float *v, float *x0, int n, int T, int D, void *stream);
+/* dx0 f32 [n*T,D] -> d_patch bf16 [n*g*g, D] (class-token rows dropped). */
+int pcg_embed_bwd(const float *dx0, const float *v, const float *gamma, void *d_patch_bf16, int n, int T, int D,
+                  void *stream);
+
+/* ---- short-sequence multi-head attention, head dim 64, no mask ------------------------------------------
+ * replaces nn.MultiheadAttention(need_weights=False) core (ruclip/model.py:43-49).
+ * qkv bf16 [n*T, 3D] (q pre-scaled), out bf16 [n*T, D], lse f32 [n, heads, T] (natural log). */
+int pcg_attn_fwd(const void *qkv, void *out, float *lse, int n, int T, int heads, void *stream);
+int pcg_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse, float *delta_ws,
+                 void *d_qkv, int n, int T, int heads, void *stream);
+
+/* ---- head: ln_post(CLS) @ proj -> L2 normalise -> spherical distance loss, forward AND gradient ---------
+ * replaces ruclip/model.py:126-129 + F.normalize (models/open_clip.py:120-121) + CLIP.forward
+ * (losses/clip/clip.py:89-99).  x f32 [n*T, D]; targets f32 [M,E]; tweights f32 [M].
+ * loss_sum: one f32, atomically += sum over this call's cutouts of sum_m w_m d(n,m) * scale.
+ * enc_out (nullable) f32 [n,E] normalised (or raw if !normalize) encodings.
+ * d_enc (nullable) f32 [n,E]: an upstream gradient w.r.t. the encodings; when given it replaces the loss
+ *   gradient (this is autograd through encode_images for callers other than the CLIP loss).
+ * dx (nullable) f32 [n*T, D]: CLS rows receive d(loss)/dx, all other rows are zeroed. dx_bf16 likewise. */
+int pcg_head_loss(const float *x, const float *ln_g, const float *ln_b, const float *proj, const float *targets,
+                  const float *tweights, int n, int T, int D, int E, int M, float scale, int normalize,
+                  float *loss_sum, float *enc_out, const float *d_enc, float *dx, void *dx_bf16, void *stream);
+
+/* ---- whole path ------------------------------------------------------------------------------------------ */
+/* bytes of scratch (transient) and stash (activations kept for backward) for n cutouts. */
+size_t pcg_workspace_bytes(const pcg_vit_config *cfg, int n_cut);
+size_t pcg_stash_bytes(const pcg_vit_config *cfg, int n_cut);
+
+typedef struct pcg_guidance_args {
+    const pcg_vit_config *cfg;
+    const pcg_vit_weights *w;
+    const float *images; int32_t B, H, W;
+    const int32_t *cuts; int32_t n_cut; int32_t max_in_w;
+    const pcg_resize_tables *tabs;
+    const float *mean_host, *std_host;
+    const float *targets, *tweights; int32_t n_targets;
+    float loss_scale;        /* multiplier / (N_total * M)                              */
+    void *workspace; size_t workspace_bytes;
+    void *stash; size_t stash_bytes;      /* may be NULL when want_grad == 0             */
+    int32_t want_grad;       /* 1: keep activations for pcg_guidance_bwd                */
+    float *loss_sum;         /* one f32, caller zeroes                                  */
+    float *enc_out;          /* nullable f32 [n_cut,E]                                  */
+    int32_t normalize;       /* L2-normalise encodings (encode_images(normalize=...))   */
+    float *d_images;         /* bwd only: f32 [B,3,H,W], caller zeroes                  */
+    const float *d_enc;      /* bwd only, nullable: f32 [n_cut,E] upstream gradient of the encodings
+                                (replaces the loss gradient; targets may then be NULL)   */
+} pcg_guidance_args;
+
+/* forward: sampler -> patch embed -> L x block -> head (+ loss).  replaces CLIP.forward end to end. */
+int pcg_guidance_fwd(const pcg_guidance_args *a, void *stream);
+/* backward to the image: replaces autograd through everything above (dgrad only; weights are frozen,
+ * perceptor/models/open_clip.py:73-76). */
+int pcg_guidance_bwd(const pcg_guidance_args *a, void *stream);
+/* number of kernels the last fwd / bwd call launched (for bench.py's gpu_launches). */
+int pcg_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCG_H_ */

@@ -1,0 +1,46 @@
+// Shared host-side plumbing for libpcg.so: error reporting across the C ABI, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pcg.h"
+
+namespace pcg {
+
+// thread-local last-error message; no C++ exception ever crosses the ABI.
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+void count_launch();
+void reset_launch_count();
+int launch_count();
+int sm_count();
+
+#define PCG_CHECK_ARG(cond, ...)                                    \
+    do {                                                            \
+        if (!(cond)) return ::pcg::set_error(-1, __VA_ARGS__);      \
+    } while (0)
+
+#define PCG_CUDA(expr)                                                                                 \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return ::pcg::set_error(static_cast<int>(_e), "%s failed: %s (%s:%d)", #expr,              \
+                                    cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+    } while (0)
+
+// after a <<<>>> launch
+#define PCG_LAUNCH_CHECK(name)                                                                         \
+    do {                                                                                               \
+        ::pcg::count_launch();                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                           \
+        if (_e != cudaSuccess)                                                                         \
+            return ::pcg::set_error(static_cast<int>(_e), "launch of %s failed: %s", name,             \
+                                    cudaGetErrorString(_e));                                           \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace pcg

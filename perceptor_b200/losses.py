@@ -1,0 +1,147 @@
+"""losses.CLIP / losses.OpenCLIP with the reference's module API, backed by the native guidance path.
+
+API parity (perceptor/losses/clip/clip.py:10-99, perceptor/losses/open_clip.py:7-97): construct with a model name,
+`add_texts_` / `add_images_` / `add_encodings_` / `add_text_off_` / `mul_` return self, `encodings` / `weights` are
+frozen nn.Parameters rebuilt by torch.cat, `forward(images[N,3,H,W])` returns a 0-d loss whose autograd gradient
+flows into `images`.  Keyword-only extras (n_cutouts, cut_pow, min_size, max_size, seed/generator, process_group)
+default to the reference behaviour: every whole image is resized and encoded.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import cutouts, models
+from .guidance import GuidanceLossFn
+
+
+class _TextImageLoss(torch.nn.Module):
+    """Shared machinery; subclasses set the reference quirks (re-normalising targets, multiplier)."""
+
+    _renormalize_targets = True
+
+    def _init_guidance(self, n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group):
+        self.n_cutouts = n_cutouts
+        self.cut_pow = float(cut_pow)
+        self.min_size = min_size
+        self.max_size = max_size
+        self.process_group = process_group
+        self.generator = generator if generator is not None else torch.Generator().manual_seed(int(seed))
+        self.encodings = None
+        self.weights = None
+        self.last_cutouts: np.ndarray | None = None
+
+    @property
+    def device(self):
+        return next(iter(self.model.parameters())).device
+
+    def add_texts_(self, texts, weights=None):
+        return self.add_encodings_(self.model.encode_texts(texts), weights)
+
+    def add_images_(self, images, weights=None):
+        with torch.no_grad():
+            return self.add_encodings_(self.model.encode_images(images), weights)
+
+    def add_encodings_(self, encodings, weights=None):
+        if isinstance(weights, (list, tuple)):
+            weights = torch.tensor(weights)
+        elif weights is None:
+            weights = torch.ones_like(encodings[:, 0])
+        encodings = encodings.detach().float()
+        if self._renormalize_targets:
+            encodings = F.normalize(encodings)
+        encodings = encodings.to(self.device)
+        weights = weights.detach().float().to(self.device)
+        if self.encodings is None:
+            self.encodings = torch.nn.Parameter(encodings, requires_grad=False)
+            self.weights = torch.nn.Parameter(weights, requires_grad=False)
+        else:
+            self.encodings = torch.nn.Parameter(torch.cat([self.encodings, encodings]), requires_grad=False)
+            self.weights = torch.nn.Parameter(torch.cat([self.weights, weights]), requires_grad=False)
+        return self
+
+    # ------------------------------------------------------------------------------------------------
+    def _cutout_rows(self, images) -> np.ndarray:
+        b, _, h, w = images.shape
+        if self.n_cutouts is None:
+            return cutouts.whole_image_cutouts(b, h, w)
+        return cutouts.sample_cutouts(self.generator, b, h, w, int(self.n_cutouts), self.cut_pow, self.min_size,
+                                      self.max_size)
+
+    def _loss(self, images, multiplier: float):
+        if self.encodings is None:
+            raise ValueError("no targets: call add_texts_/add_images_/add_encodings_ first")
+        eng = self.model.engine()
+        images = images.to(eng.device)
+        if images.dtype != torch.float32:
+            images = images.float()
+        images = images.contiguous()
+        group = self.process_group
+        rank = world = None
+        if group is not None:
+            rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+        rows = self._cutout_rows(images)
+        self.last_cutouts = rows
+        plan = eng.plan_cutouts(rows, rank or 0, world or 1)
+        targets = self.encodings.detach().to(eng.device, torch.float32).contiguous()
+        tweights = self.weights.detach().to(eng.device, torch.float32).contiguous()
+        return GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group)
+
+
+class CLIP(_TextImageLoss):
+    def __init__(self, name="ViT-B-32", precision="fp32", jit=False, *, n_cutouts=None, cut_pow=1.0, min_size=None,
+                 max_size=None, seed=0, generator=None, process_group=None, state_dict=None, weights_seed=0):
+        """
+        Args:
+            name: name of the clip model. Available models on the native path:
+                - ViT-B-32
+                - ViT-B-16
+                - ViT-L-14
+                - ViT-L-14-336
+        """
+        super().__init__()
+        self.name = name
+        extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
+        self.model = models.CLIP(name, precision, **extra)
+        self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group)
+        self.multiplier = 0.01 if name in ("ViT-L-14", "ViT-L-14-336") else 1.0
+
+    def mul_(self, multiplier):
+        self.multiplier *= multiplier
+        return self
+
+    def add_text_off_(self, weight=None, path="perceptor/losses/clip/vectors/textoff.json"):
+        textoff_json = json.loads(Path(path).read_text())
+        if self.name in textoff_json:
+            return self.add_encodings_(torch.tensor(textoff_json[self.name]), weight)
+        raise ValueError(f"There is no textoff for this model: {self.name}")
+
+    def forward(self, images):
+        return self._loss(images, self.multiplier)
+
+
+class OpenCLIP(_TextImageLoss):
+    _renormalize_targets = False  # perceptor/losses/open_clip.py:58-85 stores encodings as given
+
+    def __init__(self, architecture="ViT-L-14", weights="laion2b_s32b_b82k", *, n_cutouts=None, cut_pow=1.0,
+                 min_size=None, max_size=None, seed=0, generator=None, process_group=None, state_dict=None,
+                 weights_seed=0):
+        """
+        Args:
+            architecture (str): name of the clip model
+            weights (str): name of the weights
+
+        The reference's default (ViT-H-14, head dim 80) is outside the native path's head-dim-64 kernels.
+        """
+        super().__init__()
+        self.architecture = architecture
+        extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
+        self.model = models.OpenCLIP(architecture, weights, **extra)
+        self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group)
+
+    def forward(self, images):
+        return self._loss(images, 1.0)

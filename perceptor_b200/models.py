@@ -1,0 +1,130 @@
+"""Encoder wrappers with the reference's surface: models.CLIP(...) / models.OpenCLIP(...).
+
+Mirrors perceptor/models/clip.py:6-27 and perceptor/models/open_clip.py:11-137 for the vision side of the hot
+path: `.encode_images(images, normalize=True)`, `.image_size`, `.device`, frozen eval-mode weights.  The image
+encoder runs on the native sm_100a path (bf16 tensor-core GEMMs, fp32 residual stream / statistics); offline there
+are no pretrained weights, so weights are random-init unless a `state_dict` is supplied.
+"""
+from __future__ import annotations
+
+import weakref
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import cutouts, native
+from .guidance import EncodeImagesFn, GuidanceEngine
+from .vit import random_state_dict, required_keys, resolve_shape
+
+# (architecture, weights) pairs the reference documents for ViT towers with head dim 64
+# (perceptor/models/open_clip.py:24-44); anything else raises ValueError like the reference does (:52-53).
+_PRETRAINED = {
+    ("ViT-B-32-quickgelu", "openai"), ("ViT-B-32", "openai"), ("ViT-B-16", "openai"), ("ViT-L-14", "openai"),
+    ("ViT-L-14-336", "openai"),
+    ("ViT-B-32", "laion2b_s34b_b79k"), ("ViT-B-32", "laion2b_e16"), ("ViT-B-32", "laion400m_e32"),
+    ("ViT-B-16", "laion400m_e32"), ("ViT-L-14", "laion2b_s32b_b82k"), ("ViT-L-14", "laion400m_e32"),
+}
+
+
+class _OpenCLIP(torch.nn.Module):
+    def __init__(self, architecture="ViT-L-14", weights="openai", precision=None, *, state_dict=None, seed=0):
+        super().__init__()
+        self.architecture = architecture
+        self.weights = weights
+        if (architecture, weights) not in _PRETRAINED:
+            raise ValueError(f"Invalid architecture/weights: {architecture}/{weights}")
+        if precision not in (None, "fp32", "fp16", "bf16"):
+            raise ValueError(f"Invalid precision: {precision}")
+        # every precision maps onto the one native path: bf16 operands, fp32 accumulation / residual / statistics
+        self.precision = "bf16"
+        self.name, self.shape = resolve_shape(architecture)
+        quick = weights == "openai" or "-quickgelu" in architecture
+        self.act = native.ACT_QUICKGELU if quick else native.ACT_GELU
+        sd = state_dict if state_dict is not None else random_state_dict(self.shape, seed)
+        sd = {k[len("visual."):] if k.startswith("visual.") else k: v for k, v in sd.items()}
+        missing = [k for k in required_keys(self.shape.layers) if k not in sd]
+        if missing:
+            raise ValueError(f"state_dict is missing vision keys: {missing[:4]}...")
+        self._keys = required_keys(self.shape.layers)
+        for k in self._keys:
+            self.register_parameter(k.replace(".", "__"), torch.nn.Parameter(sd[k].detach().float(), requires_grad=False))
+        self.eval()
+        self._engines: dict[torch.device, GuidanceEngine] = {}
+        start_device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        if start_device.type == "cuda":
+            self.to(start_device)
+
+    # -- reference surface ------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return next(iter(self.parameters())).device
+
+    @property
+    def image_size(self):
+        return (self.shape.image_size, self.shape.image_size)
+
+    def state_dict_openai(self) -> dict[str, torch.Tensor]:
+        return {k: getattr(self, k.replace(".", "__")).detach() for k in self._keys}
+
+    def encode_texts(self, text_prompts, normalize=True):
+        raise NotImplementedError(
+            "the text tower is outside the accelerated hot path (SURVEY.md §8f-2); pass precomputed text "
+            "encodings to add_encodings_()")
+
+    def engine(self) -> GuidanceEngine:
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("the native CLIP image path needs a CUDA device; there is no CPU fallback")
+        dev = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        eng = self._engines.get(dev)
+        if eng is None:
+            eng = GuidanceEngine(self.shape, self.state_dict_openai(), dev, self.act)
+            self._engines = {dev: eng}  # one device at a time; drop stale packs
+        return eng
+
+    def encode_images(self, images, normalize=True, *, cutout_rows=None):
+        """[N,3,H,W] -> [N,E].  Each whole image is resized to image_size (the reference behaviour); with
+        `cutout_rows` ([n,4] int rows b,y0,x0,size) one encoding per cutout is returned instead."""
+        eng = self.engine()
+        images = images.to(eng.device)
+        if images.dtype != torch.float32:
+            images = images.float()
+        images = images.contiguous()
+        if cutout_rows is None:
+            cutout_rows = cutouts.whole_image_cutouts(images.shape[0], images.shape[2], images.shape[3])
+        plan = eng.plan_cutouts(np.asarray(cutout_rows))
+        return EncodeImagesFn.apply(images, eng, plan, bool(normalize))
+
+    @staticmethod
+    def spherical_distance(encodings_a, encodings_b):
+        return (encodings_a[:, None] - encodings_b[None, :]).norm(dim=2).div(2).arcsin().square().mul(2)
+
+    def forward(self, _):
+        raise NotImplementedError
+
+
+_cache: "weakref.WeakValueDictionary[str, _OpenCLIP]" = weakref.WeakValueDictionary()
+
+
+def OpenCLIP(architecture="ViT-L-14", weights="openai", precision=None, **kwargs):
+    """Weak-valued memoised constructor (perceptor/utils/cache.py:9-23): equal arguments share one encoder."""
+    if kwargs.get("state_dict") is not None:
+        return _OpenCLIP(architecture, weights, precision, **kwargs)
+    key = str((architecture, weights, precision)) + str(sorted(kwargs.items()))
+    model = _cache.get(key)
+    if model is None:
+        model = _OpenCLIP(architecture, weights, precision, **kwargs)
+        _cache[key] = model
+    return model
+
+
+def CLIP(architecture: str, precision=None, **kwargs):
+    """perceptor/models/clip.py:6-27: OpenAI weights; B/32 (and RN50/RN101, not covered) get `-quickgelu`."""
+    if "-quickgelu" not in architecture and architecture in ["RN50", "RN101", "ViT-B-32"]:
+        architecture = architecture + "-quickgelu"
+    return OpenCLIP(architecture, "openai", precision, **kwargs)
+
+
+def normalize_encodings(encodings: torch.Tensor) -> torch.Tensor:
+    return F.normalize(encodings)

@@ -1,0 +1,173 @@
+"""End-to-end parity on the GPU: the native guidance path (through the C ABI) against the CPU fp32 oracle.
+
+north_star tolerances: loss within 1e-2 relative, image-gradient cosine >= 0.999 (bf16 tensor-core path vs the
+fp32 reference path on the same random-init weights and inputs); cutout rows bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import guidance as guidance_oracle  # noqa: E402
+from oracle import sampler as sampler_oracle  # noqa: E402
+from perceptor_b200 import cutouts, losses, native  # noqa: E402
+from perceptor_b200.guidance import EncodeImagesFn, GuidanceEngine, GuidanceLossFn  # noqa: E402
+from perceptor_b200.vit import SHAPES, VitShape, random_state_dict  # noqa: E402
+
+LOSS_RTOL = 1e-2
+GRAD_COS = 0.999
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float(a @ b / (a.norm() * b.norm() + 1e-300))
+
+
+def perturb(sd, seed=1):
+    """make LayerNorm affine parameters and zero-init biases non-trivial so that every term is exercised"""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in sd.items():
+        if k.endswith("weight") and v.dim() == 1:
+            out[k] = v + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith("bias") or k.endswith("in_proj_bias"):
+            out[k] = v + 0.02 * torch.randn(v.shape, generator=g)
+        else:
+            out[k] = v
+    return out
+
+
+def run_case(device, shape, images, rows, m=2, multiplier=1.0, seed=0, tweights=None):
+    sd = perturb(random_state_dict(shape, seed))
+    g = torch.Generator().manual_seed(seed + 100)
+    targets = torch.nn.functional.normalize(torch.randn(m, shape.embed, generator=g))
+    tw = torch.ones(m) if tweights is None else torch.tensor(tweights, dtype=torch.float32)
+    # oracle (CPU fp32)
+    img_ref = images.clone().requires_grad_()
+    loss_ref = guidance_oracle.guidance_loss(img_ref, rows, sd, shape.image_size, shape.patch, shape.layers, shape.heads,
+                                             targets, tw, multiplier)
+    loss_ref.backward()
+    # native
+    eng = GuidanceEngine(shape, sd, device, native.ACT_QUICKGELU)
+    img = images.to(device).requires_grad_()
+    plan = eng.plan_cutouts(np.asarray(rows, dtype=np.int32))
+    loss = GuidanceLossFn.apply(img, eng, plan, targets.to(device), tw.to(device), multiplier, None)
+    loss.backward()
+    return float(loss), float(loss_ref), img.grad.cpu(), img_ref.grad, eng
+
+
+TINY = VitShape(image_size=32, patch=8, width=128, layers=2, heads=2, embed=16)
+
+
+def test_tiny_config_matches_oracle(cuda_device):
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(2, 3, 48, 40, generator=g)
+    rows = [(0, 0, 0, 40), (1, 8, 0, 32), (0, 3, 5, 20), (1, 10, 2, 37)]
+    loss, loss_ref, grad, grad_ref, _ = run_case(cuda_device, TINY, images, rows, m=3, tweights=[1.0, 0.5, -0.25])
+    assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+    assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
+
+
+def test_vit_b32_config1_matches_oracle(cuda_device):
+    """BASELINE.json configs[0]: ViT-B/32, one 3x256x256 image, 16 cutouts."""
+    shape = SHAPES["ViT-B-32"]
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(1, 3, 256, 256, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(0), 1, 256, 256, 16, 1.0, 64, 256)
+    rows_oracle = sampler_oracle.sample_cutouts(torch.Generator().manual_seed(0), 1, 256, 256, 16, 1.0, 64, 256)
+    assert rows.tolist() == [list(r) for r in rows_oracle], "cutout rows must be bit-exact"
+    loss, loss_ref, grad, grad_ref, eng = run_case(cuda_device, shape, images, rows.tolist())
+    assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+    assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
+    assert eng.launches_fwd > 0 and eng.launches_bwd > 0
+
+
+def test_vit_l14_matches_oracle(cuda_device):
+    """ViT-L/14 @224 (configs[2] shape) at a cutout count the CPU oracle finishes in seconds."""
+    shape = SHAPES["ViT-L-14"]
+    g = torch.Generator().manual_seed(1)
+    images = torch.rand(1, 3, 320, 288, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(3), 1, 320, 288, 4, 1.0, 100, 288)
+    loss, loss_ref, grad, grad_ref, _ = run_case(cuda_device, shape, images, rows.tolist(), multiplier=0.01)
+    assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+    assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
+
+
+def test_whole_image_mode_is_reference_behaviour(cuda_device):
+    """n_cutouts=None: every whole (non-square) image is resized, exactly what the reference does."""
+    g = torch.Generator().manual_seed(2)
+    images = torch.rand(2, 3, 72, 56, generator=g)
+    rows = cutouts.whole_image_cutouts(2, 72, 56)
+    loss, loss_ref, grad, grad_ref, _ = run_case(cuda_device, TINY, images, rows.tolist())
+    assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+    assert cosine(grad, grad_ref) >= GRAD_COS
+
+
+def test_encode_images_autograd(cuda_device):
+    """models.encode_images-style use: arbitrary upstream gradient on the encodings."""
+    sd = perturb(random_state_dict(TINY, 5))
+    g = torch.Generator().manual_seed(5)
+    images = torch.rand(2, 3, 40, 40, generator=g)
+    rows = [(0, 0, 0, 40, 40), (1, 0, 0, 40, 40)]
+    eng = GuidanceEngine(TINY, sd, cuda_device, native.ACT_QUICKGELU)
+    img = images.to(cuda_device).requires_grad_()
+    enc = EncodeImagesFn.apply(img, eng, eng.plan_cutouts(np.asarray(rows, dtype=np.int32)), True)
+    d_enc = torch.randn(2, TINY.embed, generator=g)
+    enc.backward(d_enc.to(cuda_device))
+    img_ref = images.clone().requires_grad_()
+    enc_ref = guidance_oracle.encode_cutouts(img_ref, rows, sd, TINY.image_size, TINY.patch, TINY.layers, TINY.heads)
+    enc_ref.backward(d_enc)
+    assert float((enc.detach().cpu() - enc_ref.detach()).abs().max()) <= 2e-2
+    assert cosine(img.grad.cpu(), img_ref.grad) >= GRAD_COS
+
+
+def test_module_api_round_trip(cuda_device):
+    """The reference's module surface: construct by name, add encodings, call, backward, detached-leaf use."""
+    loss = losses.CLIP("ViT-B-32", n_cutouts=4, min_size=64, seed=1)
+    assert loss.multiplier == 1.0 and loss.device.type == "cuda"
+    g = torch.Generator().manual_seed(0)
+    loss.add_encodings_(torch.randn(2, 512, generator=g)).add_encodings_(torch.randn(1, 512, generator=g), [0.5])
+    assert loss.encodings.shape == (3, 512) and loss.weights.tolist() == [1.0, 1.0, 0.5]
+    assert torch.allclose(loss.encodings.norm(dim=1), torch.ones(3, device=loss.device), atol=1e-6)
+    param = torch.rand(1, 3, 128, 128, generator=g).to(cuda_device).requires_grad_()
+    images = param * 1.0  # non-leaf input
+    leaf = images.detach().requires_grad_()  # gradient_checkpoint-style detached leaf
+    value = loss(leaf)
+    assert value.dim() == 0
+    value.backward()
+    images.backward(leaf.grad)
+    assert param.grad is not None and torch.isfinite(param.grad).all() and float(param.grad.abs().sum()) > 0
+    assert loss.last_cutouts.shape == (4, 4)
+    with torch.no_grad():
+        assert loss(param).dim() == 0
+    assert losses.CLIP("ViT-L-14").multiplier == 0.01
+    with pytest.raises(ValueError):
+        losses.CLIP("RN50")
+
+
+def test_full_size_properties_config2(cuda_device):
+    """BASELINE.json configs[1] at full size (ViT-B/32, 4 x 512x512, 64 cutouts/image): size-independent
+    properties — the loss is the cutout-weighted mean of per-shard losses and the gradient is additive over
+    disjoint shards of the cutout table (what the multi-GPU path relies on)."""
+    shape = SHAPES["ViT-B-32"]
+    sd = random_state_dict(shape, 0)
+    eng = GuidanceEngine(shape, sd, cuda_device, native.ACT_QUICKGELU)
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(4, 3, 512, 512, generator=g).to(cuda_device)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(0), 4, 512, 512, 64, 1.0, 64, 512)
+    targets = torch.nn.functional.normalize(torch.randn(2, 512, generator=g)).to(cuda_device)
+    tw = torch.ones(2, device=cuda_device)
+
+    def run(rank, world):
+        img = images.clone().requires_grad_()
+        plan = eng.plan_cutouts(rows, rank, world)
+        loss = GuidanceLossFn.apply(img, eng, plan, targets, tw, 1.0, None)
+        loss.backward()
+        return float(loss), img.grad
+
+    full_loss, full_grad = run(0, 1)
+    parts = [run(r, 2) for r in range(2)]
+    assert abs(sum(p[0] for p in parts) - full_loss) <= 1e-4 * abs(full_loss)
+    assert cosine(parts[0][1] + parts[1][1], full_grad) >= 0.9999
+    assert float(full_grad.abs().sum()) > 0 and torch.isfinite(full_grad).all()

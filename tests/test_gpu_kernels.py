@@ -1,0 +1,279 @@
+"""Per-kernel parity on the GPU: every C-ABI kernel against a float32 torch reference of the same op.
+
+Tolerances are stated per test; bf16 outputs are compared after the reference is computed in fp32 from the SAME
+bf16-rounded inputs, so only the output rounding (2^-9 relative) and accumulation order remain.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from perceptor_b200 import native, ops  # noqa: E402
+from perceptor_b200.resize_tables import CUBIC, LANCZOS3, choose_method  # noqa: E402
+
+bf16 = torch.bfloat16
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def check_close(got, want, rel, what):
+    assert got.shape == want.shape, f"{what}: shape {tuple(got.shape)} != {tuple(want.shape)}"
+    assert torch.isfinite(got.float()).all(), f"{what}: non-finite output"
+    e = rel_err(got, want)
+    worst = float((got.double() - want.double()).abs().max())
+    assert e <= rel, f"{what}: relative error {e:.3e} > {rel:.1e} (max abs diff {worst:.3e})"
+
+
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def dquick_gelu(x):
+    s = torch.sigmoid(1.702 * x)
+    return s * (1 + 1.702 * x * (1 - s))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 256), (256, 512, 768), (200, 768, 768), (4112, 1024, 1024), (1000, 2304, 768),
+    (784, 768, 3072), (16, 64, 64), (300, 640, 1024), (513, 3072, 768), (129, 4096, 1024), (392, 1024, 640),
+]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+def test_gemm_plain(cuda_device, m, n, k, bn):
+    g = torch.Generator(device="cpu").manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn(m, k, generator=g).to(cuda_device, bf16)
+    b = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda_device, bf16)
+    bias = torch.randn(n, generator=g).to(cuda_device)
+    want = a.float() @ b.float().t() + bias
+    got = ops.gemm(native.GEMM_F32, a, b, bias=bias, bn=bn)
+    check_close(got, want, 2e-5, f"gemm f32 {m}x{n}x{k} bn={bn}")
+    got16 = ops.gemm(native.GEMM_BF16, a, b, bias=bias, bn=bn)
+    check_close(got16, want, 4e-3, f"gemm bf16 {m}x{n}x{k} bn={bn}")
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 3072, 768), (257, 1024, 1024), (4112, 4096, 1024)])
+@pytest.mark.parametrize("act", [native.ACT_QUICKGELU, native.ACT_GELU])
+def test_gemm_epilogues(cuda_device, m, n, k, act):
+    g = torch.Generator(device="cpu").manual_seed(11 + m)
+    a = torch.randn(m, k, generator=g).to(cuda_device, bf16)
+    b = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda_device, bf16)
+    bias = torch.randn(n, generator=g).to(cuda_device)
+    acc = a.float() @ b.float().t()
+    f = quick_gelu if act == native.ACT_QUICKGELU else torch.nn.functional.gelu
+    # bias + activation
+    h, act_out = ops.gemm(native.GEMM_BIAS_ACT, a, b, bias=bias, act=act)
+    check_close(h, acc + bias, 4e-3, "bias_act: pre-activation")
+    check_close(act_out, f(acc + bias), 6e-3, "bias_act: activation")
+    # residual
+    res = torch.randn(m, n, generator=g).to(cuda_device)
+    out = ops.gemm(native.GEMM_RESID_F32, a, b, bias=bias, aux=res)
+    check_close(out, res + acc + bias, 2e-5, "residual f32")
+    # activation derivative
+    hpre = torch.randn(m, n, generator=g).to(cuda_device, bf16)
+    if act == native.ACT_QUICKGELU:
+        dact = dquick_gelu(hpre.float())
+    else:
+        x = hpre.float().requires_grad_()
+        dact = torch.autograd.grad(torch.nn.functional.gelu(x).sum(), x)[0]
+    out = ops.gemm(native.GEMM_DACT, a, b, aux=hpre, act=act)
+    check_close(out, acc * dact, 6e-3, "dact")
+
+
+def test_gemm_strided_operand(cuda_device):
+    """A read out of a wider matrix (lda > K), as the dgrad GEMMs and the padded patch matrix do."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    big = torch.randn(500, 1024, generator=g).to(cuda_device, bf16)
+    a = big[:, :640]
+    b = (torch.randn(256, 640, generator=g) / 25).to(cuda_device, bf16)
+    lib = native.lib()
+    out = torch.empty((500, 256), dtype=torch.float32, device=cuda_device)
+    native.check(lib.pcg_gemm_bf16(native.GEMM_F32, 0, 500, 256, 640, big.data_ptr(), 1024, b.data_ptr(), 640, None, None,
+                                   out.data_ptr(), None, 256, native.stream_ptr()), "gemm")
+    check_close(out, a.float() @ b.float().t(), 2e-5, "strided A")
+
+
+def test_gemm_rejects_bad_arguments(cuda_device):
+    a = torch.zeros(8, 60, dtype=bf16, device=cuda_device)
+    b = torch.zeros(32, 60, dtype=bf16, device=cuda_device)
+    with pytest.raises(ValueError):
+        ops.gemm(native.GEMM_F32, a, b)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,d", [(1, 768), (50, 768), (257 * 3, 1024), (1001, 1280), (7, 128)])
+def test_layernorm(cuda_device, rows, d):
+    g = torch.Generator(device="cpu").manual_seed(rows + d)
+    x = (torch.randn(rows, d, generator=g) * 3 + 0.5).to(cuda_device)
+    gamma = (torch.rand(d, generator=g) + 0.5).to(cuda_device)
+    beta = torch.randn(d, generator=g).to(cuda_device)
+    y = ops.layernorm_fwd(x, gamma, beta)
+    want = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5)
+    check_close(y, want, 4e-3, "layernorm fwd")
+    dy = torch.randn(rows, d, generator=g).to(cuda_device, bf16)
+    dx0 = torch.randn(rows, d, generator=g).to(cuda_device)
+    xr = x.clone().requires_grad_()
+    torch.nn.functional.layer_norm(xr, (d,), gamma, beta, 1e-5).backward(dy.float())
+    dx = dx0.clone()
+    dxb = ops.layernorm_bwd(dy, x, gamma, dx)
+    check_close(dx, dx0 + xr.grad, 1e-5, "layernorm bwd (f32 accumulate)")
+    check_close(dxb, dx0 + xr.grad, 4e-3, "layernorm bwd (bf16 copy)")
+
+
+# ------------------------------------------------------------------------------------------------ embed
+@pytest.mark.parametrize("n,grid,d", [(3, 7, 768), (2, 16, 1024), (5, 4, 128)])
+def test_embed(cuda_device, n, grid, d):
+    t = grid * grid + 1
+    g = torch.Generator(device="cpu").manual_seed(n + d)
+    patch_out = torch.randn(n * grid * grid, d, generator=g).to(cuda_device)
+    cls = torch.randn(d, generator=g).to(cuda_device)
+    pos = torch.randn(t, d, generator=g).to(cuda_device)
+    gamma = (torch.rand(d, generator=g) + 0.5).to(cuda_device)
+    beta = torch.randn(d, generator=g).to(cuda_device)
+    pr = patch_out.clone().requires_grad_()
+    v_ref = torch.cat([cls.expand(n, 1, d), pr.reshape(n, grid * grid, d)], dim=1) + pos
+    x_ref = torch.nn.functional.layer_norm(v_ref, (d,), gamma, beta, 1e-5)
+    v, x0 = ops.embed_fwd(patch_out, cls, pos, gamma, beta, n, t)
+    check_close(v, v_ref.reshape(n * t, d), 1e-6, "embed v")
+    check_close(x0, x_ref.reshape(n * t, d), 1e-5, "embed x0")
+    dx0 = torch.randn(n * t, d, generator=g).to(cuda_device)
+    x_ref.backward(dx0.reshape(n, t, d))
+    got = ops.embed_bwd(dx0, v, gamma, n, t)
+    check_close(got, pr.grad, 4e-3, "embed bwd")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attn_reference(qkv, n, t, heads):
+    d = heads * 64
+    q, k, v = (z.reshape(n, t, heads, 64).transpose(1, 2) for z in qkv.float().reshape(n, t, 3 * d).chunk(3, dim=-1))
+    s = q @ k.transpose(-1, -2)  # q is pre-scaled
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(n * t, d)
+    return o, torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("n,t,heads", [(2, 50, 12), (1, 197, 12), (3, 257, 16), (1, 577, 16), (2, 17, 2), (1, 64, 2),
+                                       (1, 65, 2), (2, 128, 1)])
+def test_attention(cuda_device, n, t, heads):
+    d = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(t + heads)
+    qkv = torch.randn(n * t, 3 * d, generator=g)
+    qkv[:, :d] *= 0.25  # pre-scaled queries, logits O(1)
+    qkv = qkv.to(cuda_device, bf16)
+    out, lse = ops.attn_fwd(qkv, n, t, heads)
+    ref = qkv.float().clone().requires_grad_()
+    o_ref, lse_ref = attn_reference(ref, n, t, heads)
+    check_close(out, o_ref, 6e-3, f"attention fwd T={t}")
+    check_close(lse, lse_ref, 1e-3, f"attention lse T={t}")
+    d_out = torch.randn(n * t, d, generator=g).to(cuda_device, bf16)
+    o_ref.backward(d_out.float())
+    d_qkv = ops.attn_bwd(qkv, out, d_out, lse, n, t, heads)
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        check_close(d_qkv[:, sl], ref.grad[:, sl], 1.5e-2, f"attention {name} T={t}")
+
+
+# ------------------------------------------------------------------------------------------------ head
+def head_reference(x, ln_g, ln_b, proj, targets, tw, n, t, scale, normalize=True):
+    d = x.shape[1]
+    cls = x.reshape(n, t, d)[:, 0, :]
+    z = torch.nn.functional.layer_norm(cls, (d,), ln_g, ln_b, 1e-5) @ proj
+    e = torch.nn.functional.normalize(z) if normalize else z
+    dist = (e[:, None] - targets[None, :]).norm(dim=2).div(2).arcsin().square().mul(2)
+    return (dist * tw).sum() * scale, e
+
+
+@pytest.mark.parametrize("n,t,d,e,m", [(4, 50, 768, 512, 2), (3, 257, 1024, 768, 3), (2, 17, 128, 16, 1)])
+def test_head_loss(cuda_device, n, t, d, e, m):
+    g = torch.Generator(device="cpu").manual_seed(n + d + m)
+    x = torch.randn(n * t, d, generator=g).to(cuda_device)
+    ln_g = (torch.rand(d, generator=g) + 0.5).to(cuda_device)
+    ln_b = (torch.randn(d, generator=g) * 0.1).to(cuda_device)
+    proj = (torch.randn(d, e, generator=g) * d**-0.5).to(cuda_device)
+    targets = torch.nn.functional.normalize(torch.randn(m, e, generator=g)).to(cuda_device)
+    tw = torch.tensor([1.0, -0.5, 2.0][:m]).to(cuda_device)
+    scale = 0.01 / (n * m)
+    xr = x.clone().requires_grad_()
+    loss_ref, e_ref = head_reference(xr, ln_g, ln_b, proj, targets, tw, n, t, scale)
+    loss_ref.backward()
+    loss, enc, dx, dxb = ops.head_loss(x, ln_g, ln_b, proj, targets, tw, n, t, scale)
+    check_close(enc, e_ref.detach(), 1e-5, "head encodings")
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)) + 1e-9, (float(loss), float(loss_ref))
+    check_close(dx, xr.grad, 2e-4, "head dx")
+    check_close(dxb, xr.grad, 4e-3, "head dx bf16")
+    # upstream-gradient mode (autograd through encode_images)
+    d_enc = torch.randn(n, e, generator=g).to(cuda_device)
+    xr2 = x.clone().requires_grad_()
+    _, e2 = head_reference(xr2, ln_g, ln_b, proj, targets, tw, n, t, 1.0)
+    e2.backward(d_enc)
+    _, _, dx2, _ = ops.head_loss(x, ln_g, ln_b, proj, None, None, n, t, 1.0, d_enc=d_enc)
+    check_close(dx2, xr2.grad, 2e-4, "head dx from d_enc")
+
+
+def test_head_loss_edge_cases(cuda_device):
+    """target == own encoding (r = 0: zero subgradient, like torch.norm) and antipodal target (r = 2)."""
+    n, t, d, e = 2, 5, 128, 16
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(n * t, d, generator=g).to(cuda_device)
+    ln_g = torch.ones(d, device=cuda_device)
+    ln_b = torch.zeros(d, device=cuda_device)
+    proj = (torch.randn(d, e, generator=g) * d**-0.5).to(cuda_device)
+    _, enc, _, _ = ops.head_loss(x, ln_g, ln_b, proj, None, None, n, t, want_grad=False)
+    for targets, want_loss in ((enc[:1].clone(), None), (-enc[:1].clone(), None)):
+        tw = torch.ones(1, device=cuda_device)
+        loss, _, dx, _ = ops.head_loss(x, ln_g, ln_b, proj, targets, tw, n, t, 1.0)
+        assert torch.isfinite(loss).all() and torch.isfinite(dx).all()
+    loss0, _, dx0, _ = ops.head_loss(x[: t], ln_g, ln_b, proj, enc[:1].clone(), torch.ones(1, device=cuda_device), 1, t, 1.0)
+    assert float(loss0) < 1e-6 and float(dx0.abs().max()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+def sampler_reference(images, rows5, r):
+    """float64 application of the product's own tap tables is covered on CPU; here compare with the oracle."""
+    from oracle import resize as resize_oracle
+
+    outs = []
+    for b, y0, x0, h, w in rows5:
+        outs.append(resize_oracle.resize(images[b:b + 1, :, y0:y0 + h, x0:x0 + w], (r, r)))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("r,patch", [(224, 32), (224, 14), (336, 14)])
+def test_sampler_forward_backward(cuda_device, r, patch):
+    g = torch.Generator(device="cpu").manual_seed(r + patch)
+    images = torch.rand(2, 3, 400, 520, generator=g)
+    rows = [(0, 0, 0, 400, 520), (1, 10, 20, 300, 300), (0, 100, 200, 225, 225), (1, 50, 60, 100, 100),
+            (0, 7, 9, r, r), (1, 0, 100, 390, 150), (0, 176, 296, 224, 224), (1, 3, 5, 33, 47)]
+    rows = np.array(rows, dtype=np.int32)
+    methods = [choose_method(int(h), int(w), r, r) for h, w in rows[:, 3:5]]
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    smp = ops.Sampler(r, patch, cuda_device, mean, std)
+    patches, out = smp.forward(images.to(cuda_device), rows, methods)
+    img_ref = images.clone().requires_grad_()
+    ref = sampler_reference(img_ref, rows, r)
+    ref_n = (ref - torch.tensor(mean).reshape(1, 3, 1, 1)) / torch.tensor(std).reshape(1, 3, 1, 1)
+    assert float((out.cpu() - ref_n.detach()).abs().max()) <= 2e-5, "sampler forward (f32) vs oracle resize"
+    # patch-major bf16 operand == im2col of the f32 output
+    gsz = r // patch
+    n = rows.shape[0]
+    im2col = out.reshape(n, 3, gsz, patch, gsz, patch).permute(0, 2, 4, 1, 3, 5).reshape(n * gsz * gsz, 3 * patch * patch)
+    assert torch.equal(patches[:, : 3 * patch * patch], im2col.to(bf16)), "patch-major layout"
+    assert float(patches[:, 3 * patch * patch:].float().abs().max() if patches.shape[1] > 3 * patch * patch else 0.0) == 0
+    # backward: f32 upstream gradient
+    d_out = torch.randn(n, 3, r, r, generator=g)
+    ref_n.backward(d_out)
+    d_img = smp.backward(tuple(images.shape), rows, methods, d_out=d_out.to(cuda_device))
+    check_close(d_img.cpu(), img_ref.grad, 1e-5, "sampler backward (f32 in)")
+    # backward: bf16 patch-major upstream gradient
+    d_p = torch.zeros_like(patches)
+    d_p[:, : 3 * patch * patch] = d_out.reshape(n, 3, gsz, patch, gsz, patch).permute(0, 2, 4, 1, 3, 5).reshape(
+        n * gsz * gsz, -1).to(cuda_device, bf16)
+    d_img2 = smp.backward(tuple(images.shape), rows, methods, d_patches=d_p)
+    check_close(d_img2.cpu(), img_ref.grad, 4e-3, "sampler backward (bf16 patches in)")
