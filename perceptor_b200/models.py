@@ -107,14 +107,14 @@ class _OpenCLIP(torch.nn.Module):
 _cache: "weakref.WeakValueDictionary[str, _OpenCLIP]" = weakref.WeakValueDictionary()
 
 
-def OpenCLIP(architecture="ViT-L-14", weights="openai", precision=None, **kwargs):
+def OpenCLIP(architecture="ViT-L-14", weights="openai", precision=None, *, state_dict=None, seed=0):
     """Weak-valued memoised constructor (perceptor/utils/cache.py:9-23): equal arguments share one encoder."""
-    if kwargs.get("state_dict") is not None:
-        return _OpenCLIP(architecture, weights, precision, **kwargs)
-    key = str((architecture, weights, precision)) + str(sorted(kwargs.items()))
+    if state_dict is not None:
+        return _OpenCLIP(architecture, weights, precision, state_dict=state_dict)
+    key = str((architecture, weights, precision, int(seed)))
     model = _cache.get(key)
     if model is None:
-        model = _OpenCLIP(architecture, weights, precision, **kwargs)
+        model = _OpenCLIP(architecture, weights, precision, seed=seed)
         _cache[key] = model
     return model
 
