@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — CLIP-guidance throughput (loss forward + backward to the image), cutouts/s.
+
+    python bench.py --gpus N --steps K --warmup W            # native sm_100a path
+    python bench.py --impl reference --gpus N ...             # the reference algorithm on the host CPU cores
+    torchrun --nproc-per-node N bench.py --gpus N ...         # N > 1: one rank per GPU over NCCL
+
+Workload (BASELINE.json metric: "ViT-L/14 ... at 1/2/4/8 B200", configs[2]): ViT-L/14 @224, random-init weights,
+N_gpu synthetic 3x512x512 images, 128 random cutouts per image, 2 random targets; the cutout table is sharded over
+the ranks (one image's worth of cutouts per GPU => weak scaling) and the per-image gradient is summed with one NCCL
+all-reduce.  One step = sample cutouts -> loss forward -> backward to images.grad.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (architecture, image H=W, cutouts per image, min cutout size, images per GPU)
+    "vit_l14_224_128cut_512px": ("ViT-L-14", 512, 128, 128, 1),
+    "vit_b32_224_64cut_4x512px": ("ViT-B-32", 512, 64, 64, 4),
+    "vit_l14_336_256cut_768px": ("ViT-L-14-336", 768, 256, 192, 1),
+    "vit_b32_224_16cut_256px": ("ViT-B-32", 256, 16, 64, 1),
+}
+DEFAULT_WORKLOAD = "vit_l14_224_128cut_512px"
+METRIC = "CLIP-guidance cutouts/sec (loss + image grad), ViT-L/14, at 1/2/4/8 B200"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load": samples drawing noticeably more than idle power
+        hot = [s for s, p in zip(sm, power) if p > 300.0] or sm
+        return {"sm_mhz": statistics.median(hot) if hot else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step_fn(arch: str, hw: int, min_size: int, sample_cutouts: int):
+    """Returns a closure running one loss+backward over `sample_cutouts` cutouts with the CPU oracle."""
+    from oracle import guidance as guidance_oracle
+    from oracle import loss as loss_oracle
+    from perceptor_b200 import cutouts
+    from perceptor_b200.vit import SHAPES, random_state_dict
+
+    shape = SHAPES[arch]
+    sd = random_state_dict(shape, 0)
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(1, 3, hw, hw, generator=g)
+    targets = torch.nn.functional.normalize(torch.randn(2, shape.embed, generator=g))
+    weights = torch.ones(2)
+    gen = torch.Generator().manual_seed(0)
+    mult = loss_oracle.default_multiplier(arch)
+
+    def step():
+        rows = cutouts.sample_cutouts(gen, 1, hw, hw, sample_cutouts, 1.0, min_size, hw)
+        img = images.clone().requires_grad_()
+        loss = guidance_oracle.guidance_loss(img, rows.tolist(), sd, shape.image_size, shape.patch, shape.layers,
+                                             shape.heads, targets, weights, mult)
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def time_cpu(arch, hw, min_size, sample_cutouts, steps, warmup, budget_s=25.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn(arch, hw, min_size, sample_cutouts)
+    for _ in range(warmup):
+        step()
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    med = statistics.median(times)
+    return sample_cutouts / med, med, len(times)
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    arch, hw, n_cut, min_size, imgs = WORKLOADS[args.workload]
+    sample = args.cpu_sample
+    value, med, done = time_cpu(arch, hw, min_size, sample, max(args.steps, 1), min(args.warmup, 1), budget_s=120.0)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "cutouts/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": arch, "image": f"{hw}x{hw}", "cutouts_per_image": n_cut,
+                   "note": f"each step is a bounded sample of {sample} cutouts of this workload on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": "cutouts/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} cutouts/step, {done} steps, median; fp32 torch CPU oracle "
+                                   f"(reference resize_right + ruclip ViT restated), {os.cpu_count()} host cpus"},
+        "e2e": {"value": value, "unit": "cutouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------------------
+def run_native(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+
+    from perceptor_b200 import losses, native
+    from perceptor_b200.vit import SHAPES
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native guidance path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+
+    arch, hw, n_cut, min_size, imgs_per_gpu = WORKLOADS[args.workload]
+    shape = SHAPES[arch]
+    n_images = imgs_per_gpu * world
+    cutouts_per_step = n_images * n_cut
+
+    loss_mod = losses.CLIP(arch, n_cutouts=n_cut, min_size=min_size, max_size=hw, seed=0, process_group=group)
+    g = torch.Generator().manual_seed(0)
+    loss_mod.add_encodings_(torch.randn(2, shape.embed, generator=g))
+    eng = loss_mod.model.engine()
+    eng.prebuild_tables(min_size, hw)
+    host_images = torch.rand(n_images, 3, hw, hw, generator=g).pin_memory()
+    dev_images = host_images.to(device)
+    host_grad = torch.empty_like(host_images).pin_memory()
+
+    def step_device():
+        img = dev_images.detach().requires_grad_()
+        loss = loss_mod(img)
+        loss.backward()
+        return loss, img.grad
+
+    def step_e2e():
+        img = host_images.to(device, non_blocking=True).requires_grad_()
+        loss = loss_mod(img)
+        loss.backward()
+        host_grad.copy_(img.grad, non_blocking=True)
+        return float(loss)  # D2H read of the scalar; synchronises the step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    lib = native.lib()
+    profile = rank == 0
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    if profile:
+        lib.pcg_profile_enable(1)
+        native.profile_collect()
+    total_ms = timed(step_device, args.steps)
+    prof = native.profile_collect() if profile else None
+    lib.pcg_profile_enable(0)
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = cutouts_per_step / (ms_per_step * 1e-3)
+    launches = args.steps * (eng.launches_fwd + eng.launches_bwd)
+
+    # end to end through the public module API with HOST buffers (H2D of the images, D2H of loss + gradient)
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(2, min(args.steps, 10))
+    e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e_value = cutouts_per_step / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    flops_per_cutout = shape.flops_per_cutout()
+    step_tflops = value / world * flops_per_cutout / 1e12
+    gemm = prof["gemm"]
+    gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    families = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["count"] / args.steps,
+                    "rate": (v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("gemm", "attn_fwd", "attn_bwd") else 1e9))
+                    if v["ms"] > 0 else 0.0} for k, v in prof.items()}
+
+    cpu_value, cpu_med, cpu_done = time_cpu(arch, hw, min_size, args.cpu_sample, 2, 1) if not args.no_cpu else (None, None, 0)
+    line = {
+        "metric": METRIC, "value": value, "unit": "cutouts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "model": arch, "images": n_images, "image": f"{hw}x{hw}",
+                   "cutouts_per_image": n_cut, "cutouts_per_step": cutouts_per_step, "targets": 2,
+                   "parallelism": f"cutout-sharded dp{world}" if world > 1 else "single GPU",
+                   "weights": "random-init (no network for checkpoints)",
+                   "l2": "per-step working set (activation stash >= 19 GB for ViT-L/14 x128) >> 126 MB L2; no flush needed",
+                   "step_tflops_per_gpu": step_tflops, "step_frac_of_peak": step_tflops / peak,
+                   "kernel_families": families},
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": "cutouts/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": host_images.numel() * 4 + cutouts_per_step // world * 32,
+                "d2h_bytes_per_step": host_grad.numel() * 4 + 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": gemm_tflops, "peak": peak,
+                     "unit": "TFLOP/s", "frac": gemm_tflops / peak, "traffic": None,
+                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                     "launches_timed": gemm["count"], "share_of_step": gemm["ms"] / total_ms},
+    }
+    if cpu_value is not None:
+        line["cpu_baseline"] = {"value": cpu_value, "unit": "cutouts/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_sample} cutouts/step of the same workload, {cpu_done} timed steps "
+                                          f"(median {cpu_med:.2f} s), fp32 torch CPU oracle, {os.cpu_count()} host cpus"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument("--cpu-sample", type=int, default=8, help="cutouts per CPU-baseline step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -183,6 +183,15 @@ int pcg_guidance_bwd(const pcg_guidance_args *a, void *stream);
 /* number of kernels the last fwd / bwd call launched (for bench.py's gpu_launches). */
 int pcg_last_launch_count(void);
 
+/* ---- diagnostics: device-side timing per kernel family (CUDA events on the launch stream) -------------- */
+enum {
+    PCG_PROF_GEMM = 0, PCG_PROF_ATTN_FWD = 1, PCG_PROF_ATTN_BWD = 2, PCG_PROF_LAYERNORM = 3, PCG_PROF_SAMPLER_FWD = 4,
+    PCG_PROF_SAMPLER_BWD = 5, PCG_PROF_EMBED = 6, PCG_PROF_HEAD = 7, PCG_PROF_KINDS = 8
+};
+int pcg_profile_enable(int on);
+/* ms/work/count: arrays of PCG_PROF_KINDS; work = algorithmic FLOPs (GEMM, attention) or bytes (the rest). */
+int pcg_profile_collect(double *ms, double *work, int *count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@
 // (perceptor/models/ruclip/model.py:105-131) and the autograd tape behind it.
 #include <string.h>
 
+#include <vector>
+
 #include "pcg_common.cuh"
 
 namespace pcg {
@@ -34,6 +36,26 @@ int sm_count() {
         return n;
     }();
     return sms;
+}
+
+// ---- optional device-side timing of kernel families ----------------------------------------------------
+struct ProfRecord {
+    int kind;
+    double work;
+    cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+void profile_begin(int kind, double work, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    ProfRecord r{kind, work, nullptr, nullptr};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, stream);
+    g_prof.push_back(r);
+}
+void profile_end(cudaStream_t stream) {
+    if (!g_prof_on || g_prof.empty()) return;
+    cudaEventRecord(g_prof.back().e1, stream);
 }
 
 namespace {
@@ -176,6 +198,29 @@ extern "C" const char* pcg_last_error(void) { return last_error_buf(); }
 extern "C" int pcg_abi_version(void) { return PCG_ABI_VERSION; }
 extern "C" int pcg_device_sm_count(void) { return sm_count(); }
 extern "C" int pcg_last_launch_count(void) { return launch_count(); }
+
+extern "C" int pcg_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+// Sums the records since the last collect into ms[kind], work[kind], count[kind] (arrays of PCG_PROF_KINDS).
+extern "C" int pcg_profile_collect(double* ms, double* work, int* count) {
+    PCG_CHECK_ARG(ms && work && count, "pcg_profile_collect: null output");
+    for (int i = 0; i < PCG_PROF_KINDS; ++i) ms[i] = work[i] = 0.0, count[i] = 0;
+    for (ProfRecord& r : g_prof) {
+        float t = 0.f;
+        if (r.e0 && r.e1 && cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess &&
+            r.kind >= 0 && r.kind < PCG_PROF_KINDS) {
+            ms[r.kind] += t;
+            work[r.kind] += r.work;
+            count[r.kind] += 1;
+        }
+        if (r.e0) cudaEventDestroy(r.e0);
+        if (r.e1) cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    return 0;
+}
 
 extern "C" size_t pcg_workspace_bytes(const pcg_vit_config* cfg, int n_cut) {
     if (cfg == nullptr || n_cut <= 0) return 0;

@@ -539,6 +539,7 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     PCG_CHECK_ARG(n > 0 && T > 0 && heads > 0, "pcg_attn_fwd: bad shape n=%d T=%d heads=%d", n, T, heads);
     PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "pcg_attn_fwd: n and heads must be <= 65535");
     const dim3 grid(ceil_div(T, kTile), heads, n);
+    ProfileScope prof(PCG_PROF_ATTN_FWD, 4.0 * T * T * kHd * heads * n, static_cast<cudaStream_t>(stream));
     attn_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, T, heads);
     PCG_LAUNCH_CHECK("attn_fwd_kernel");
@@ -561,6 +562,7 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
         configured = true;
     }
     const int rows = n * T;
+    ProfileScope prof(PCG_PROF_ATTN_BWD, 8.0 * T * T * kHd * heads * n, s);
     const long long warps = static_cast<long long>(rows) * heads;
     attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(
         static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta_ws, rows, T, heads);

@@ -406,6 +406,7 @@ int gemm_bf16_impl(int mode, int act, int M, int N, int K, const void* A, int ld
     rc = get_tensor_map(&mb, B, N, K, ldb, bn);
     if (rc) return rc;
     GemmParams p{M, N, K, bias, aux, out, out2, ldo, act};
+    ProfileScope prof(PCG_PROF_GEMM, 2.0 * M * N * K, stream);
     switch (bn) {
         case 256: return dispatch_mode<256>(mode, ma, mb, p, stream);
         case 192: return dispatch_mode<192>(mode, ma, mb, p, stream);

@@ -40,6 +40,16 @@ int sm_count();
                                     cudaGetErrorString(_e));                                           \
     } while (0)
 
+// Optional per-kernel-family device timing (CUDA events on the launch stream), off by default.
+// kinds: see PCG_PROF_* in include/pcg.h.  `work` is algorithmic FLOPs (tensor-bound kinds) or bytes (HBM-bound).
+void profile_begin(int kind, double work, cudaStream_t stream);
+void profile_end(cudaStream_t stream);
+struct ProfileScope {
+    cudaStream_t s;
+    ProfileScope(int kind, double work, cudaStream_t stream) : s(stream) { profile_begin(kind, work, stream); }
+    ~ProfileScope() { profile_end(s); }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

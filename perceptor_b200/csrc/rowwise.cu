@@ -351,6 +351,7 @@ extern "C" int pcg_layernorm_fwd(const float* x, const float* gamma, const float
                                  void* stream) {
     PCG_CHECK_ARG(x && gamma && beta && y_bf16 && rows > 0, "pcg_layernorm_fwd: bad arguments");
     if (int rc = check_d("pcg_layernorm_fwd", D)) return rc;
+    ProfileScope prof(PCG_PROF_LAYERNORM, 6.0 * rows * D, static_cast<cudaStream_t>(stream));
     layernorm_fwd_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, gamma, beta, static_cast<bf16*>(y_bf16), rows, D);
     PCG_LAUNCH_CHECK("layernorm_fwd_kernel");
@@ -361,6 +362,7 @@ extern "C" int pcg_layernorm_bwd(const void* dy_bf16, const float* x, const floa
                                  int rows, int D, void* stream) {
     PCG_CHECK_ARG(dy_bf16 && x && gamma && dx_io && dx_bf16 && rows > 0, "pcg_layernorm_bwd: bad arguments");
     if (int rc = check_d("pcg_layernorm_bwd", D)) return rc;
+    ProfileScope prof(PCG_PROF_LAYERNORM, 16.0 * rows * D, static_cast<cudaStream_t>(stream));
     layernorm_bwd_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows, D);
     PCG_LAUNCH_CHECK("layernorm_bwd_kernel");
@@ -371,6 +373,7 @@ extern "C" int pcg_embed_fwd(const float* patch_out, const float* cls, const flo
                              const float* beta, float* v, float* x0, int n, int T, int D, void* stream) {
     PCG_CHECK_ARG(patch_out && cls && pos && gamma && beta && v && x0 && n > 0 && T > 1, "pcg_embed_fwd: bad arguments");
     if (int rc = check_d("pcg_embed_fwd", D)) return rc;
+    ProfileScope prof(PCG_PROF_EMBED, 12.0 * n * T * D, static_cast<cudaStream_t>(stream));
     embed_fwd_kernel<<<ceil_div(n * T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(patch_out, cls, pos, gamma, beta,
                                                                                           v, x0, n, T, D);
     PCG_LAUNCH_CHECK("embed_fwd_kernel");
@@ -381,6 +384,7 @@ extern "C" int pcg_embed_bwd(const float* dx0, const float* v, const float* gamm
                              int D, void* stream) {
     PCG_CHECK_ARG(dx0 && v && gamma && d_patch_bf16 && n > 0 && T > 1, "pcg_embed_bwd: bad arguments");
     if (int rc = check_d("pcg_embed_bwd", D)) return rc;
+    ProfileScope prof(PCG_PROF_EMBED, 10.0 * n * T * D, static_cast<cudaStream_t>(stream));
     embed_bwd_kernel<<<ceil_div(n * (T - 1), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dx0, v, gamma, static_cast<bf16*>(d_patch_bf16), n, T, D);
     PCG_LAUNCH_CHECK("embed_bwd_kernel");
@@ -397,6 +401,7 @@ extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t smem = static_cast<size_t>(2 * D + 2 * E) * sizeof(float);
     PCG_CHECK_ARG(smem <= 48 * 1024, "pcg_head_loss: D=%d E=%d exceed the shared-memory budget", D, E);
+    ProfileScope prof(PCG_PROF_HEAD, (dx ? 6.0 : 0.0) * n * T * D + 8.0 * n * D * E, s);
     if (dx != nullptr) {
         PCG_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(n) * T * D * sizeof(float), s));
         if (dx_bf16 != nullptr) PCG_CUDA(cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(n) * T * D * 2, s));

@@ -203,6 +203,7 @@ extern "C" int pcg_sampler_fwd(const float* images, int B, int H, int W, const i
         configured = true;
     }
     const dim3 grid(ceil_div(R, p.RB), 3, n_cut);
+    ProfileScope prof(PCG_PROF_SAMPLER_FWD, 6.0 * n_cut * R * R, static_cast<cudaStream_t>(stream));
     sampler_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p, static_cast<bf16*>(patches_bf16),
                                                                                     out_f32);
     PCG_LAUNCH_CHECK("sampler_fwd_kernel");
@@ -228,6 +229,7 @@ extern "C" int pcg_sampler_bwd(const void* d_patches_bf16, const float* d_out_f3
         configured = true;
     }
     const dim3 grid(ceil_div(R, p.RB), 3, n_cut);
+    ProfileScope prof(PCG_PROF_SAMPLER_BWD, 6.0 * n_cut * R * R, static_cast<cudaStream_t>(stream));
     sampler_bwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         p, static_cast<const bf16*>(d_patches_bf16), d_out_f32, d_images);
     PCG_LAUNCH_CHECK("sampler_bwd_kernel");

@@ -93,7 +93,18 @@ SIGNATURES = {
     "pcg_stash_bytes": (C.c_size_t, [C.POINTER(VitConfig), _i]),
     "pcg_guidance_fwd": (_i, [C.POINTER(GuidanceArgs), _vp]),
     "pcg_guidance_bwd": (_i, [C.POINTER(GuidanceArgs), _vp]),
+    "pcg_profile_enable": (_i, [_i]),
+    "pcg_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }
+PROF_KINDS = ("gemm", "attn_fwd", "attn_bwd", "layernorm", "sampler_fwd", "sampler_bwd", "embed", "head")
+
+
+def profile_collect() -> dict:
+    """{family: {"ms": .., "work": .., "count": ..}} since the last collect (pcg_profile_enable(1) first)."""
+    n = len(PROF_KINDS)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int * n)()
+    check(lib().pcg_profile_collect(ms, work, cnt), "pcg_profile_collect")
+    return {k: {"ms": ms[i], "work": work[i], "count": cnt[i]} for i, k in enumerate(PROF_KINDS)}
 # test hook, not part of the public header
 _EXTRA = {"pcg_gemm_bf16_bn": (_i, [_i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp])}
 
