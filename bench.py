@@ -125,7 +125,7 @@ def cpu_step_fn(arch: str, hw: int, min_size: int, sample_cutouts: int):
         loss = guidance_oracle.guidance_loss(img, rows.tolist(), sd, shape.image_size, shape.patch, shape.layers,
                                              shape.heads, targets, weights, mult)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
