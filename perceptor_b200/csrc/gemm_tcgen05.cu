@@ -4,8 +4,9 @@
 //     forward GEMMs consume weights as stored and the dgrad GEMMs consume pre-transposed copies.
 //   * TMA (cp.async.bulk.tensor, 128-byte swizzle) stages 128 x 64 (A) and BN x 64 (B) tiles through an
 //     mbarrier ring; one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered
-//     fp32 accumulator in tensor memory; eight epilogue warps drain it with tcgen05.ld and apply the fused
-//     epilogue (bias / QuickGELU / residual add / activation derivative) straight from registers.
+//     fp32 accumulator in tensor memory; eight epilogue warps drain it with tcgen05.ld, transpose each 32 x 32
+//     chunk through a swizzled shared-memory tile and apply the fused epilogue (bias / QuickGELU / residual add /
+//     activation derivative) with fully coalesced global loads and stores; epilogue inputs are prefetched ahead.
 //   * grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x + i*gridDim.x (n fastest so that the CTAs
 //     running concurrently share A row-panels in L2; B (weights) is L2 resident).
 //
@@ -30,14 +31,17 @@ constexpr int kCtrlWarps = 4;  // warp 0: TMA producer, warp 1: MMA issuer, warp
 constexpr int kEpiWarps = 8;   // two warpgroups; warp%4 selects the TMEM lane quarter, warpgroup the column half
 constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
 constexpr int kABytes = BM * BK * 2;
+constexpr int kEpiStageBytes = 32 * 32 * 4;  // per epilogue warp: one 32 x 32 fp32 chunk, XOR-swizzled 16-byte columns
 
 template <int BN>
 struct TileCfg {
     static constexpr int kBBytes = BN * BK * 2;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmem = kStages * (kABytes + kBBytes) + kBarBytes + 1024;  // +1024: manual alignment
+    static constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;
+    static constexpr int kSmem = kStages * (kABytes + kBBytes) + kEpiBytes + kBarBytes + 1024;  // +1024: manual alignment
+    static_assert(kSmem <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 struct GemmParams {
@@ -50,19 +54,33 @@ struct GemmParams {
     int act;
 };
 
-__device__ __forceinline__ float act_fwd(float h, int act) {
-    if (act == PCG_ACT_QUICKGELU) return __fdividef(h, 1.0f + __expf(-1.702f * h));
-    return 0.5f * h * (1.0f + erff(h * 0.70710678118654752f));
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ float act_bwd(float h, int act) {
-    if (act == PCG_ACT_QUICKGELU) {
-        const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * h));
-        return s * (1.0f + 1.702f * h * (1.0f - s));
+// QuickGELU x * sigmoid(1.702 x) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU.TANH + 3 FMA-class ops.
+// The activation is a template parameter so that erff never bloats the QuickGELU kernels' instruction footprint.
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float h) {
+    if constexpr (ACT == PCG_ACT_QUICKGELU) {
+        const float hh = 0.5f * h;
+        return fmaf(hh, tanh_approx(0.851f * h), hh);
+    } else {
+        return 0.5f * h * (1.0f + erff(h * 0.70710678118654752f));
     }
-    return 0.5f * (1.0f + erff(h * 0.70710678118654752f)) + h * 0.3989422804014327f * __expf(-0.5f * h * h);
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd(float h) {
+    if constexpr (ACT == PCG_ACT_QUICKGELU) {
+        const float s = fmaf(0.5f, tanh_approx(0.851f * h), 0.5f);
+        return s * fmaf(1.702f * h, 1.0f - s, 1.0f);
+    } else {
+        return 0.5f * (1.0f + erff(h * 0.70710678118654752f)) + h * 0.3989422804014327f * __expf(-0.5f * h * h);
+    }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p) {
@@ -76,7 +94,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes));
+    uint8_t* smem_epi = smem + kStages * (kABytes + kBBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
     uint64_t* tfull_bar = bars + 2 * kStages;
@@ -168,97 +187,110 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp >= kCtrlWarps) {
-        // ===================== epilogue warps =====================
-        const int quarter = warp & 3;             // TMEM lanes [32*quarter, +32) are the ones this warp may read
+        // TMEM -> registers (thread = row) -> XOR-swizzled per-warp staging tile in smem -> registers
+        // (8 lanes = one row's 32 columns) so that every global access is a full, coalesced row segment.
+        // Epilogue inputs (residual / pre-activation) are prefetched kDist 32-column chunks ahead, across tile
+        // boundaries, to keep >= 64 KB of reads in flight per SM (the epilogue is latency-, not throughput-bound).
+        const int quarter = warp & 3;               // TMEM lanes [32*quarter, +32) are the ones this warp may read
         const int half = (warp - kCtrlWarps) >> 2;  // column half of the tile
         constexpr int kHalfN = BN / 2;
+        constexpr int kChunks = kHalfN / 32;
+        constexpr bool kHasAux = (MODE == PCG_GEMM_RESID_F32 || MODE == PCG_GEMM_DACT);
+        constexpr int kAuxWords = (MODE == PCG_GEMM_RESID_F32) ? 4 : 2;  // 32-bit words per lane per row group
+        constexpr int kDistWanted = (MODE == PCG_GEMM_RESID_F32) ? 2 : 4;
+        // the slot of chunk c must be a compile-time constant: kDist has to divide kChunks
+        constexpr int kDist = !kHasAux ? 1 : (kChunks % kDistWanted == 0 ? kDistWanted : (kChunks % 2 == 0 ? 2 : kChunks));
+        uint8_t* stage_buf = smem_epi + (warp - kCtrlWarps) * kEpiStageBytes;
+        const int sub_row = lane >> 3;  // row within a 4-row group when reading back
+        const int sub_col = lane & 7;   // 16-byte column chunk (4 floats) within the 32-column chunk
+        uint32_t auxr[kDist][8][kAuxWords];
+        // issue the loads of chunk `c` of tile `t` into slot `c % kDist`
+        auto prefetch_aux = [&](int t, int c, uint32_t(&dst)[8][kAuxWords]) {
+            if constexpr (kHasAux) {
+                if (t < num_tiles) {
+                    const int rb = (t / num_n) * BM + quarter * 32 + sub_row;
+                    const int col = (t % num_n) * BN + half * kHalfN + c * 32 + sub_col * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int grow = rb + i * 4;
+                        if (grow < p.M && col < p.N) {
+                            const size_t off = static_cast<size_t>(grow) * p.ldo + col;
+                            if constexpr (MODE == PCG_GEMM_RESID_F32) {
+                                const uint4 t4 = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.aux) + off);
+                                dst[i][0] = t4.x; dst[i][1] = t4.y; dst[i][kAuxWords - 2] = t4.z; dst[i][kAuxWords - 1] = t4.w;
+                            } else {
+                                const uint2 t2 = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.aux) + off);
+                                dst[i][0] = t2.x; dst[i][1] = t2.y;
+                            }
+                        }
+                    }
+                }
+            }
+        };
+#pragma unroll
+        for (int d = 0; d < kDist; ++d) prefetch_aux(static_cast<int>(blockIdx.x) + (d / kChunks) * gridDim.x, d % kChunks, auxr[d % kDist]);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
+            const int row_base = m0 + quarter * 32;
+            const int col_base = n0 + half * kHalfN + sub_col * 4;  // this lane's first column of chunk 0
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-            const int grow = m0 + quarter * 32 + lane;
-            const bool row_ok = grow < p.M;
-            const size_t row_off = static_cast<size_t>(grow) * p.ldo;
-#pragma unroll 1
-            for (int c = 0; c < kHalfN; c += 32) {
-                const int col0 = n0 + half * kHalfN + c;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * kHalfN + c,
-                              r);
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * kHalfN;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr0, r);
+#pragma unroll  // fully unrolled: registers of an in-flight tcgen05.ld must not be carried around a loop back-edge
+            for (int c = 0; c < kChunks; ++c) {
+                const int col = col_base + c * 32;
                 tmem_wait_ld();
-                if (row_ok && col0 < p.N) {
-                    float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias != nullptr) {
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                if (c + 1 < kChunks) tmem_ld_32x32(taddr0 + (c + 1) * 32, r);  // in flight while chunk c is written out
+                __syncwarp();
+                const bool col_ok = col < p.N;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                            v[j] += b.x;
-                            v[j + 1] += b.y;
-                            v[j + 2] += b.z;
-                            v[j + 3] += b.w;
+                for (int i = 0; i < 8; ++i) {
+                    const int lrow = i * 4 + sub_row;
+                    const int grow = row_base + lrow;
+                    float4 v = *reinterpret_cast<const float4*>(stage_buf + lrow * 128 + ((sub_col ^ (lrow & 7)) << 4));
+                    if (grow < p.M && col_ok) {
+                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                        const size_t off = static_cast<size_t>(grow) * p.ldo + col;
+                        const uint32_t(&ax)[kAuxWords] = auxr[c % kDist][i];
+                        if constexpr (MODE == PCG_GEMM_BF16) {
+                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) =
+                                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                        } else if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
+                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) =
+                                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out2) + off) =
+                                make_uint2(pack_bf16(act_fwd<ACT>(v.x), act_fwd<ACT>(v.y)),
+                                           pack_bf16(act_fwd<ACT>(v.z), act_fwd<ACT>(v.w)));
+                        } else if constexpr (MODE == PCG_GEMM_RESID_F32) {
+                            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) =
+                                make_float4(__uint_as_float(ax[0]) + v.x, __uint_as_float(ax[1]) + v.y,
+                                            __uint_as_float(ax[kAuxWords - 2]) + v.z, __uint_as_float(ax[kAuxWords - 1]) + v.w);
+                        } else if constexpr (MODE == PCG_GEMM_DACT) {
+                            const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&ax[0]);
+                            const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&ax[1]);
+                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) = make_uint2(
+                                pack_bf16(v.x * act_bwd<ACT>(__low2float(h01)), v.y * act_bwd<ACT>(__high2float(h01))),
+                                pack_bf16(v.z * act_bwd<ACT>(__low2float(h23)), v.w * act_bwd<ACT>(__high2float(h23))));
+                        } else {  // PCG_GEMM_F32
+                            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
                         }
-                    }
-                    if constexpr (MODE == PCG_GEMM_BF16) {
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                                                pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    } else if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + col0);
-                        uint4* dst2 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + row_off + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                                                pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst2[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                                                 pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    } else if constexpr (MODE == PCG_GEMM_RESID_F32) {
-                        const float4* res = reinterpret_cast<const float4*>(static_cast<const float*>(p.aux) + row_off + col0);
-                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 x = res[j];
-                            dst[j] = make_float4(x.x + v[4 * j], x.y + v[4 * j + 1], x.z + v[4 * j + 2],
-                                                 x.w + v[4 * j + 3]);
-                        }
-                    } else if constexpr (MODE == PCG_GEMM_DACT) {
-                        const uint4* hp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux) + row_off + col0);
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + col0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 hv = hp[j];
-                            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&hw[q]);
-                                v[8 * j + 2 * q] *= act_bwd(__low2float(h2), p.act);
-                                v[8 * j + 2 * q + 1] *= act_bwd(__high2float(h2), p.act);
-                            }
-                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]),
-                                                pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                        }
-                    } else {  // PCG_GEMM_F32
-                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 }
+                // slot c % kDist is free again: prefetch the chunk kDist items ahead (possibly of a later tile)
+                prefetch_aux(tile + ((c + kDist) / kChunks) * static_cast<int>(gridDim.x), (c + kDist) % kChunks, auxr[c % kDist]);
+                __syncwarp();  // staging tile is rewritten by the next chunk
             }
             tc_fence_before();
             __syncwarp();
@@ -336,20 +368,27 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
     return 0;
 }
 
-template <int BN, int MODE>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int MODE, int ACT>
+int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
     using Cfg = TileCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmem));
         configured = true;
     }
     const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_tcgen05_kernel<BN, MODE><<<grid, kThreads, Cfg::kSmem, stream>>>(ma, mb, p);
+    gemm_tcgen05_kernel<BN, MODE, ACT><<<grid, kThreads, Cfg::kSmem, stream>>>(ma, mb, p);
     PCG_LAUNCH_CHECK("gemm_tcgen05_kernel");
     return 0;
+}
+template <int BN, int MODE>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+    if constexpr (MODE == PCG_GEMM_BIAS_ACT || MODE == PCG_GEMM_DACT) {
+        if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU>(ma, mb, p, stream);
+    }
+    return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU>(ma, mb, p, stream);
 }
 
 template <int BN>
@@ -423,6 +462,7 @@ extern "C" int pcg_gemm_bf16(int mode, int act, int M, int N, int K, const void*
     return pcg::gemm_bf16_impl(mode, act, M, N, K, A, lda, B, ldb, bias, aux, out, out2, ldo, 0,
                                static_cast<cudaStream_t>(stream));
 }
+extern "C" int pcg_gemm_set_variant(int) { return 0; }  // kept for tools; there is a single epilogue variant now
 // test hook: force the N tile width (64/128/192/256)
 extern "C" int pcg_gemm_bf16_bn(int bn, int mode, int act, int M, int N, int K, const void* A, int lda, const void* B,
                                 int ldb, const float* bias, const void* aux, void* out, void* out2, int ldo,

@@ -106,7 +106,8 @@ def profile_collect() -> dict:
     check(lib().pcg_profile_collect(ms, work, cnt), "pcg_profile_collect")
     return {k: {"ms": ms[i], "work": work[i], "count": cnt[i]} for i, k in enumerate(PROF_KINDS)}
 # test hook, not part of the public header
-_EXTRA = {"pcg_gemm_bf16_bn": (_i, [_i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp])}
+_EXTRA = {"pcg_gemm_bf16_bn": (_i, [_i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+          "pcg_gemm_set_variant": (_i, [_i])}
 
 _lib = None
 
