@@ -108,7 +108,7 @@ __device__ __forceinline__ void store_tile_bf16(const float (&acc)[8][4], bf16* 
 // forward
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                       float* __restrict__ lse, int T, int heads) {
+                                                       float* __restrict__ lse, int T, int heads, int q_begin) {
     __shared__ __align__(128) bf16 sQ[kTile * kHd];
     __shared__ __align__(128) bf16 sK[2][kTile * kHd];
     __shared__ __align__(128) bf16 sV[2][kTile * kHd];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
     const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
     const int D = heads * kHd, ld = 3 * D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = qt * kTile;
+    const int q0 = q_begin + qt * kTile;  // rows below q_begin belong to the tcgen05 kernel
     const bf16* gq = qkv + static_cast<size_t>(n) * T * ld + h * kHd;
     const bf16* gk = gq + D;
     const bf16* gv = gq + 2 * D;
@@ -290,14 +290,14 @@ __device__ __forceinline__ void load_vec_async(float* sdst, const float* gsrc, i
 __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out,
                                                             const float* __restrict__ lse,
                                                             const float* __restrict__ delta,
-                                                            bf16* __restrict__ d_qkv, int T, int heads) {
+                                                            bf16* __restrict__ d_qkv, int T, int heads, int k_begin) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_dyn);
 
     const int kt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
     const int D = heads * kHd, ld = 3 * D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k0 = kt * kTile;
+    const int k0 = k_begin + kt * kTile;  // keys below k_begin belong to the tcgen05 kernel
     const bf16* gq = qkv + static_cast<size_t>(n) * T * ld + h * kHd;
     const bf16* gk = gq + D;
     const bf16* gv = gq + 2 * D;
@@ -419,14 +419,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out,
                                                           const float* __restrict__ lse,
                                                           const float* __restrict__ delta, bf16* __restrict__ d_qkv,
-                                                          int T, int heads) {
+                                                          int T, int heads, int q_begin) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_dyn);  // kv[] holds Q / dO here; q[] / d_o[] hold K / V tiles
 
     const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
     const int D = heads * kHd, ld = 3 * D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = qt * kTile;
+    const int q0 = q_begin + qt * kTile;
     const bf16* gq = qkv + static_cast<size_t>(n) * T * ld + h * kHd;
     const bf16* gk = gq + D;
     const bf16* gv = gq + 2 * D;
@@ -533,26 +533,30 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
 }  // namespace
 }  // namespace pcg
 
-extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T, int heads, void* stream) {
-    using namespace pcg;
-    PCG_CHECK_ARG(qkv && out && lse, "pcg_attn_fwd: null pointer");
-    PCG_CHECK_ARG(n > 0 && T > 0 && heads > 0, "pcg_attn_fwd: bad shape n=%d T=%d heads=%d", n, T, heads);
-    PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "pcg_attn_fwd: n and heads must be <= 65535");
-    const dim3 grid(ceil_div(T, kTile), heads, n);
-    ProfileScope prof(PCG_PROF_ATTN_FWD, 4.0 * T * T * kHd * heads * n, static_cast<cudaStream_t>(stream));
-    attn_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, T, heads);
+namespace pcg {
+
+// mma.sync path for query rows [q_begin, T) (everything when q_begin == 0)
+int attn_fwd_legacy(const void* qkv, void* out, float* lse, int n, int T, int heads, int q_begin, cudaStream_t s) {
+    if (q_begin >= T) return 0;
+    const dim3 grid(ceil_div(T - q_begin, kTile), heads, n);
+    attn_fwd_kernel<<<grid, 128, 0, s>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, T, heads, q_begin);
     PCG_LAUNCH_CHECK("attn_fwd_kernel");
     return 0;
 }
 
-extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
-                            void* d_qkv, int n, int T, int heads, void* stream) {
-    using namespace pcg;
-    PCG_CHECK_ARG(qkv && out && d_out && lse && delta_ws && d_qkv, "pcg_attn_bwd: null pointer");
-    PCG_CHECK_ARG(n > 0 && T > 0 && heads > 0, "pcg_attn_bwd: bad shape n=%d T=%d heads=%d", n, T, heads);
-    PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "pcg_attn_bwd: n and heads must be <= 65535");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+int attn_delta(const void* out, const void* d_out, float* delta, int n, int T, int heads, cudaStream_t s) {
+    const int rows = n * T;
+    const long long warps = static_cast<long long>(rows) * heads;
+    attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(
+        static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta, rows, T, heads);
+    PCG_LAUNCH_CHECK("attn_delta_kernel");
+    return 0;
+}
+
+// mma.sync backward for key rows [k_begin, T) (dK, dV) and query rows [q_begin, T) (dQ); delta must be ready
+int attn_bwd_legacy(const void* qkv, const void* d_out, const float* lse, const float* delta, void* d_qkv, int n, int T,
+                    int heads, int begin, cudaStream_t s) {
+    if (begin >= T) return 0;
     static bool configured = false;
     if (!configured) {
         PCG_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -561,19 +565,14 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
                                       static_cast<int>(sizeof(BwdSmem))));
         configured = true;
     }
-    const int rows = n * T;
-    ProfileScope prof(PCG_PROF_ATTN_BWD, 8.0 * T * T * kHd * heads * n, s);
-    const long long warps = static_cast<long long>(rows) * heads;
-    attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(
-        static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta_ws, rows, T, heads);
-    PCG_LAUNCH_CHECK("attn_delta_kernel");
-    const dim3 grid(ceil_div(T, kTile), heads, n);
-    attn_bwd_dkdv_kernel<<<grid, 128, sizeof(BwdSmem), s>>>(static_cast<const bf16*>(qkv),
-                                                           static_cast<const bf16*>(d_out), lse, delta_ws,
-                                                           static_cast<bf16*>(d_qkv), T, heads);
+    const dim3 grid(ceil_div(T - begin, kTile), heads, n);
+    attn_bwd_dkdv_kernel<<<grid, 128, sizeof(BwdSmem), s>>>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_out),
+                                                           lse, delta, static_cast<bf16*>(d_qkv), T, heads, begin);
     PCG_LAUNCH_CHECK("attn_bwd_dkdv_kernel");
     attn_bwd_dq_kernel<<<grid, 128, sizeof(BwdSmem), s>>>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_out),
-                                                         lse, delta_ws, static_cast<bf16*>(d_qkv), T, heads);
+                                                         lse, delta, static_cast<bf16*>(d_qkv), T, heads, begin);
     PCG_LAUNCH_CHECK("attn_bwd_dq_kernel");
     return 0;
 }
+
+}  // namespace pcg
