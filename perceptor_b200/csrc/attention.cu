@@ -250,19 +250,34 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 // backward, pass 0: delta[n,h,t] = sum_d dO * O
 // ---------------------------------------------------------------------------------------------------------
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
-                                  int n_rows, int T, int heads) {
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (row, head)
-    const int lane = threadIdx.x & 31;
-    if (gw >= n_rows * heads) return;
-    const int row = gw / heads, h = gw % heads;
-    const size_t off = static_cast<size_t>(row) * heads * kHd + h * kHd + lane * 2;
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + off);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(d_o + off);
-    float v = __low2float(a) * __low2float(b) + __high2float(a) * __high2float(b);
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                                                         float* __restrict__ delta, int n_rows, int T, int heads) {
+    // 8 lanes x 16 bytes cover the 64 dims of one (row, head); a warp handles 4 consecutive (row, head) pairs
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long pair = gid >> 3;
+    const int sub = threadIdx.x & 7;
+    const bool ok = pair < static_cast<long long>(n_rows) * heads;
+    float v = 0.f;
+    int row = 0, h = 0;
+    if (ok) {
+        row = static_cast<int>(pair / heads);
+        h = static_cast<int>(pair % heads);
+        const size_t off = static_cast<size_t>(row) * heads * kHd + h * kHd + sub * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(o + off);
+        const uint4 b = *reinterpret_cast<const uint4*>(d_o + off);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (lane == 0) {
+        for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&aw[q]);
+            const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(&bw[q]);
+            v = fmaf(__low2float(x), __low2float(y), v);
+            v = fmaf(__high2float(x), __high2float(y), v);
+        }
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (ok && sub == 0) {
         const int nn = row / T, t = row % T;
         delta[(static_cast<size_t>(nn) * heads + h) * T + t] = v;
     }
@@ -287,7 +302,7 @@ __device__ __forceinline__ void load_vec_async(float* sdst, const float* gsrc, i
     }
 }
 
-__global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out,
+__global__ void __launch_bounds__(128, 3) attn_bwd_dkdv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out,
                                                             const float* __restrict__ lse,
                                                             const float* __restrict__ delta,
                                                             bf16* __restrict__ d_qkv, int T, int heads, int k_begin) {
@@ -315,7 +330,6 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
     load_vec_async(sm.delta[0], gdel, 0, T, 0.f);
 
     const bool warp_active = (k0 + warp * 16) < T;
-    uint32_t kf[4][4], vf[4][4];
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -336,67 +350,78 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
         }
         __syncthreads();
         if (warp_active) {
-            if (i == 0) {
-                load_a_frags(kf, sm.kv[0], warp * 16);
-                load_a_frags(vf, sm.kv[1], warp * 16);
-            }
             const int valid = min(kTile, T - i * kTile);  // valid queries in this tile
             const int npair = (valid + 15) >> 4;
-            float st[8][4], dpt[8][4];
+            // two halves of 32 query columns each: halves the live S^T / dP^T registers (3 CTAs per SM instead of 2)
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int half = 0; half < 2; ++half) {
+                if (2 * half < npair) {
+                    float st[4][4], dpt[4][4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) st[a][c] = dpt[a][c] = 0.f;
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int pair = 0; pair < 4; ++pair) {
-                if (pair < npair) {
+                        for (int c = 0; c < 4; ++c) st[a][c] = dpt[a][c] = 0.f;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        uint32_t b[4];
-                        load_b_nk(b, sm.q[buf], pair, ks);
-                        mma_bf16_16816(st[2 * pair], kf[ks], b[0], b[1]);
-                        mma_bf16_16816(st[2 * pair + 1], kf[ks], b[2], b[3]);
-                        load_b_nk(b, sm.d_o[buf], pair, ks);
-                        mma_bf16_16816(dpt[2 * pair], vf[ks], b[0], b[1]);
-                        mma_bf16_16816(dpt[2 * pair + 1], vf[ks], b[2], b[3]);
+                        // A fragments of this warp's 16 keys are re-read from shared memory instead of being pinned
+                        uint32_t ka[4], va[4];
+                        {
+                            const int row = warp * 16 + (lane & 15), col = ks * 16 + ((lane >> 4) << 3);
+                            ldmatrix_x4(ka, smem_u32(sm.kv[0]) + swz(row, col));
+                            ldmatrix_x4(va, smem_u32(sm.kv[1]) + swz(row, col));
+                        }
+#pragma unroll
+                        for (int pp = 0; pp < 2; ++pp) {
+                            const int pair = 2 * half + pp;
+                            if (pair < npair) {
+                                uint32_t b[4];
+                                load_b_nk(b, sm.q[buf], pair, ks);
+                                mma_bf16_16816(st[2 * pp], ka, b[0], b[1]);
+                                mma_bf16_16816(st[2 * pp + 1], ka, b[2], b[3]);
+                                load_b_nk(b, sm.d_o[buf], pair, ks);
+                                mma_bf16_16816(dpt[2 * pp], va, b[0], b[1]);
+                                mma_bf16_16816(dpt[2 * pp + 1], va, b[2], b[3]);
+                            }
+                        }
                     }
-                }
-            }
-            // P^T and dS^T (columns are queries)
+                    // P^T and dS^T (columns are queries)
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const int col = nt * 8 + ((lane & 3) << 1);
-                const float l0 = sm.lse[buf][col], l1 = sm.lse[buf][col + 1];
-                const float d0 = sm.delta[buf][col], d1 = sm.delta[buf][col + 1];
-                const float p0 = exp2f((st[nt][0] - l0) * kLog2e), p1 = exp2f((st[nt][1] - l1) * kLog2e);
-                const float p2 = exp2f((st[nt][2] - l0) * kLog2e), p3 = exp2f((st[nt][3] - l1) * kLog2e);
-                st[nt][0] = p0; st[nt][1] = p1; st[nt][2] = p2; st[nt][3] = p3;
-                dpt[nt][0] = p0 * (dpt[nt][0] - d0);
-                dpt[nt][1] = p1 * (dpt[nt][1] - d1);
-                dpt[nt][2] = p2 * (dpt[nt][2] - d0);
-                dpt[nt][3] = p3 * (dpt[nt][3] - d1);
-            }
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int col = half * 32 + nt * 8 + ((lane & 3) << 1);
+                        const float l0 = sm.lse[buf][col], l1 = sm.lse[buf][col + 1];
+                        const float d0 = sm.delta[buf][col], d1 = sm.delta[buf][col + 1];
+                        const float p0 = exp2f((st[nt][0] - l0) * kLog2e), p1 = exp2f((st[nt][1] - l1) * kLog2e);
+                        const float p2 = exp2f((st[nt][2] - l0) * kLog2e), p3 = exp2f((st[nt][3] - l1) * kLog2e);
+                        st[nt][0] = p0; st[nt][1] = p1; st[nt][2] = p2; st[nt][3] = p3;
+                        dpt[nt][0] = p0 * (dpt[nt][0] - d0);
+                        dpt[nt][1] = p1 * (dpt[nt][1] - d1);
+                        dpt[nt][2] = p2 * (dpt[nt][2] - d0);
+                        dpt[nt][3] = p3 * (dpt[nt][3] - d1);
+                    }
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                if (ks < npair) {
-                    uint32_t pa[4], da[4];
-                    pa[0] = pack_bf16(st[2 * ks][0], st[2 * ks][1]);
-                    pa[1] = pack_bf16(st[2 * ks][2], st[2 * ks][3]);
-                    pa[2] = pack_bf16(st[2 * ks + 1][0], st[2 * ks + 1][1]);
-                    pa[3] = pack_bf16(st[2 * ks + 1][2], st[2 * ks + 1][3]);
-                    da[0] = pack_bf16(dpt[2 * ks][0], dpt[2 * ks][1]);
-                    da[1] = pack_bf16(dpt[2 * ks][2], dpt[2 * ks][3]);
-                    da[2] = pack_bf16(dpt[2 * ks + 1][0], dpt[2 * ks + 1][1]);
-                    da[3] = pack_bf16(dpt[2 * ks + 1][2], dpt[2 * ks + 1][3]);
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int ks = 2 * half + pp;  // k-step over queries
+                        if (ks < npair) {
+                            uint32_t pa[4], da[4];
+                            pa[0] = pack_bf16(st[2 * pp][0], st[2 * pp][1]);
+                            pa[1] = pack_bf16(st[2 * pp][2], st[2 * pp][3]);
+                            pa[2] = pack_bf16(st[2 * pp + 1][0], st[2 * pp + 1][1]);
+                            pa[3] = pack_bf16(st[2 * pp + 1][2], st[2 * pp + 1][3]);
+                            da[0] = pack_bf16(dpt[2 * pp][0], dpt[2 * pp][1]);
+                            da[1] = pack_bf16(dpt[2 * pp][2], dpt[2 * pp][3]);
+                            da[2] = pack_bf16(dpt[2 * pp + 1][0], dpt[2 * pp + 1][1]);
+                            da[3] = pack_bf16(dpt[2 * pp + 1][2], dpt[2 * pp + 1][3]);
 #pragma unroll
-                    for (int dp = 0; dp < 4; ++dp) {
-                        uint32_t b[4];
-                        load_b_kn(b, sm.d_o[buf], dp, ks);
-                        mma_bf16_16816(dv[2 * dp], pa, b[0], b[1]);
-                        mma_bf16_16816(dv[2 * dp + 1], pa, b[2], b[3]);
-                        load_b_kn(b, sm.q[buf], dp, ks);
-                        mma_bf16_16816(dk[2 * dp], da, b[0], b[1]);
-                        mma_bf16_16816(dk[2 * dp + 1], da, b[2], b[3]);
+                            for (int dp = 0; dp < 4; ++dp) {
+                                uint32_t b[4];
+                                load_b_kn(b, sm.d_o[buf], dp, ks);
+                                mma_bf16_16816(dv[2 * dp], pa, b[0], b[1]);
+                                mma_bf16_16816(dv[2 * dp + 1], pa, b[2], b[3]);
+                                load_b_kn(b, sm.q[buf], dp, ks);
+                                mma_bf16_16816(dk[2 * dp], da, b[0], b[1]);
+                                mma_bf16_16816(dk[2 * dp + 1], da, b[2], b[3]);
+                            }
+                        }
                     }
                 }
             }
@@ -546,8 +571,8 @@ int attn_fwd_legacy(const void* qkv, void* out, float* lse, int n, int T, int he
 
 int attn_delta(const void* out, const void* d_out, float* delta, int n, int T, int heads, cudaStream_t s) {
     const int rows = n * T;
-    const long long warps = static_cast<long long>(rows) * heads;
-    attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>(
+    const long long threads = static_cast<long long>(rows) * heads * 8;
+    attn_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(
         static_cast<const bf16*>(out), static_cast<const bf16*>(d_out), delta, rows, T, heads);
     PCG_LAUNCH_CHECK("attn_delta_kernel");
     return 0;

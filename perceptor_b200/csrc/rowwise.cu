@@ -1,7 +1,9 @@
 // Row-wise HBM-bound kernels of the ViT: LayerNorm forward/backward on the fp32 residual stream (bf16 GEMM operand
 // out), class-token + positional-embedding + ln_pre assembly, and the fused head
 // (ln_post(CLS) @ proj -> L2 normalise -> spherical-distance loss, forward and analytic gradient in one launch).
-// One warp per row, float4 loads, warp-shuffle reductions, fp32 statistics (recomputed in backward, not stored).
+// One warp per row, float4 loads issued up front (all of a row's traffic is in flight before the first reduction),
+// warp-shuffle reductions, fp32 statistics (recomputed in backward, not stored).  Templated on D/128 so that the
+// per-lane row slice lives in exactly-sized register arrays.
 //
 // Replaces LayerNorm (perceptor/models/ruclip/model.py:11-17), the cat/pos-emb/ln_pre sequence (:109-120),
 // ln_post + proj (:126-129), F.normalize (perceptor/models/open_clip.py:120-121) and CLIP.forward's distance
@@ -15,6 +17,8 @@ namespace {
 using bf16 = __nv_bfloat16;
 constexpr int kMaxV = 12;  // float4 per lane: supports D <= 1536, D % 128 == 0
 constexpr float kLnEps = 1e-5f;
+constexpr int kRowThreads = 128;  // 4 rows per block
+constexpr int kRowsPerBlock = kRowThreads / 32;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -26,21 +30,21 @@ struct RowStats {
     float mean, rstd;
 };
 
-// x[] holds this lane's float4s (nv of them); returns mean / rstd of the whole row (biased variance, eps 1e-5)
-__device__ __forceinline__ RowStats row_stats(const float4 (&x)[kMaxV], int nv, int D) {
+// x[] holds this lane's float4s; returns mean / rstd of the whole row (biased variance, eps 1e-5)
+template <int NV>
+__device__ __forceinline__ RowStats row_stats(const float4 (&x)[NV]) {
+    constexpr float inv_d = 1.0f / (NV * 128);
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
-    const float mean = warp_sum(s) / D;
+    for (int i = 0; i < NV; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    const float mean = warp_sum(s) * inv_d;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-        }
-    const float var = warp_sum(q) / D;
+    for (int i = 0; i < NV; ++i) {
+        const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = warp_sum(q) * inv_d;
     return {mean, 1.0f / sqrtf(var + kLnEps)};
 }
 
@@ -51,54 +55,53 @@ __device__ __forceinline__ uint2 pack4(float a, float b, float c, float d) {
 // --------------------------------------------------------------------------------------------------------
 // LayerNorm forward: y(bf16) = (x - mean) * rstd * gamma + beta
 // --------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, bf16* __restrict__ y,
-                                                            int rows, int D) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, bf16* __restrict__ y,
+                                                                    int rows) {
+    constexpr int D = NV * 128;
+    const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const int nv = D >> 7;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-    float4 v[kMaxV];
+    float4 v[NV];
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) v[i] = xr[i * 32 + lane];
-    const RowStats st = row_stats(v, nv, D);
+    for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+    const RowStats st = row_stats<NV>(v);
     uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
-            yr[i * 32 + lane] = pack4((v[i].x - st.mean) * st.rstd * g.x + b.x, (v[i].y - st.mean) * st.rstd * g.y + b.y,
-                                      (v[i].z - st.mean) * st.rstd * g.z + b.z, (v[i].w - st.mean) * st.rstd * g.w + b.w);
-        }
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+        yr[i * 32 + lane] = pack4((v[i].x - st.mean) * st.rstd * g.x + b.x, (v[i].y - st.mean) * st.rstd * g.y + b.y,
+                                  (v[i].z - st.mean) * st.rstd * g.z + b.z, (v[i].w - st.mean) * st.rstd * g.w + b.w);
+    }
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
-__device__ __forceinline__ void ln_bwd_row(const float4 (&x)[kMaxV], float4 (&g)[kMaxV], const float* gamma, int nv,
-                                           int D, int lane) {
-    const RowStats st = row_stats(x, nv, D);
+template <int NV>
+__device__ __forceinline__ void ln_bwd_row(const float4 (&x)[NV], float4 (&g)[NV], const float* gamma, int lane) {
+    constexpr float inv_d = 1.0f / (NV * 128);
+    const RowStats st = row_stats<NV>(x);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-            g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
-            s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-            s2 += g[i].x * (x[i].x - st.mean) + g[i].y * (x[i].y - st.mean) + g[i].z * (x[i].z - st.mean) +
-                  g[i].w * (x[i].w - st.mean);
-        }
-    const float c1 = warp_sum(s1) / D;
-    const float c2 = warp_sum(s2) * st.rstd / D;  // mean(g * xhat)
+    for (int i = 0; i < NV; ++i) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+        g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += g[i].x * (x[i].x - st.mean) + g[i].y * (x[i].y - st.mean) + g[i].z * (x[i].z - st.mean) +
+              g[i].w * (x[i].w - st.mean);
+    }
+    const float c1 = warp_sum(s1) * inv_d;
+    const float c2 = warp_sum(s2) * st.rstd * inv_d;  // mean(g * xhat)
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            g[i].x = st.rstd * (g[i].x - c1 - (x[i].x - st.mean) * st.rstd * c2);
-            g[i].y = st.rstd * (g[i].y - c1 - (x[i].y - st.mean) * st.rstd * c2);
-            g[i].z = st.rstd * (g[i].z - c1 - (x[i].z - st.mean) * st.rstd * c2);
-            g[i].w = st.rstd * (g[i].w - c1 - (x[i].w - st.mean) * st.rstd * c2);
-        }
+    for (int i = 0; i < NV; ++i) {
+        g[i].x = st.rstd * (g[i].x - c1 - (x[i].x - st.mean) * st.rstd * c2);
+        g[i].y = st.rstd * (g[i].y - c1 - (x[i].y - st.mean) * st.rstd * c2);
+        g[i].z = st.rstd * (g[i].z - c1 - (x[i].z - st.mean) * st.rstd * c2);
+        g[i].w = st.rstd * (g[i].w - c1 - (x[i].w - st.mean) * st.rstd * c2);
+    }
 }
 
 __device__ __forceinline__ float4 bf16x4_to_float4(uint2 u) {
@@ -107,98 +110,109 @@ __device__ __forceinline__ float4 bf16x4_to_float4(uint2 u) {
     return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
 }
 
-// dx_io += LN_bwd(dy) ; dx_bf16 = bf16(dx_io)
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ gamma, float* __restrict__ dx_io,
-                                                            bf16* __restrict__ dx_bf16, int rows, int D) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+// dx_io += LN_bwd(dy) ; dx_bf16 = bf16(dx_io).  All three input streams are requested before the first reduction.
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+                                                                    const float* __restrict__ gamma,
+                                                                    float* __restrict__ dx_io, bf16* __restrict__ dx_bf16,
+                                                                    int rows) {
+    constexpr int D = NV * 128;
+    const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const int nv = D >> 7;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
-    float4 v[kMaxV], g[kMaxV];
-#pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            v[i] = xr[i * 32 + lane];
-            g[i] = bf16x4_to_float4(dyr[i * 32 + lane]);
-        }
-    ln_bwd_row(v, g, gamma, nv, D, lane);
     float4* dxr = reinterpret_cast<float4*>(dx_io + static_cast<size_t>(row) * D);
+    float4 v[NV], g[NV], acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = xr[i * 32 + lane];
+        g[i] = bf16x4_to_float4(dyr[i * 32 + lane]);
+        acc[i] = dxr[i * 32 + lane];
+    }
+    ln_bwd_row<NV>(v, g, gamma, lane);
     uint2* dbr = reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(row) * D);
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            float4 d = dxr[i * 32 + lane];
-            d.x += g[i].x; d.y += g[i].y; d.z += g[i].z; d.w += g[i].w;
-            dxr[i * 32 + lane] = d;
-            dbr[i * 32 + lane] = pack4(d.x, d.y, d.z, d.w);
-        }
+    for (int i = 0; i < NV; ++i) {
+        const float4 d = make_float4(acc[i].x + g[i].x, acc[i].y + g[i].y, acc[i].z + g[i].z, acc[i].w + g[i].w);
+        dxr[i * 32 + lane] = d;
+        dbr[i * 32 + lane] = pack4(d.x, d.y, d.z, d.w);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------
 // embed: v = (t == 0 ? cls : patch_out[n*g*g + t-1]) + pos[t];  x0 = ln_pre(v)
 // --------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls,
-                                                        const float* __restrict__ pos, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float* __restrict__ vout,
-                                                        float* __restrict__ x0, int n, int T, int D) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads) embed_fwd_kernel(const float* __restrict__ patch_out,
+                                                                const float* __restrict__ cls, const float* __restrict__ pos,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ vout, float* __restrict__ x0, int n, int T) {
+    constexpr int D = NV * 128;
+    const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n * T) return;
     const int nn = row / T, t = row % T;
-    const int nv = D >> 7;
     const float4* src = (t == 0) ? reinterpret_cast<const float4*>(cls)
                                  : reinterpret_cast<const float4*>(patch_out + (static_cast<size_t>(nn) * (T - 1) + (t - 1)) * D);
     const float4* pr = reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * D);
-    float4 v[kMaxV];
+    float4 v[NV];
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            const float4 a = src[i * 32 + lane];
-            const float4 b = __ldg(pr + i * 32 + lane);
-            v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-        }
-    const RowStats st = row_stats(v, nv, D);
+    for (int i = 0; i < NV; ++i) {
+        const float4 a = src[i * 32 + lane];
+        const float4 b = __ldg(pr + i * 32 + lane);
+        v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    const RowStats st = row_stats<NV>(v);
     float4* vr = reinterpret_cast<float4*>(vout + static_cast<size_t>(row) * D);
     float4* xr = reinterpret_cast<float4*>(x0 + static_cast<size_t>(row) * D);
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
-            vr[i * 32 + lane] = v[i];
-            xr[i * 32 + lane] = make_float4((v[i].x - st.mean) * st.rstd * g.x + b.x, (v[i].y - st.mean) * st.rstd * g.y + b.y,
-                                            (v[i].z - st.mean) * st.rstd * g.z + b.z, (v[i].w - st.mean) * st.rstd * g.w + b.w);
-        }
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+        vr[i * 32 + lane] = v[i];
+        xr[i * 32 + lane] = make_float4((v[i].x - st.mean) * st.rstd * g.x + b.x, (v[i].y - st.mean) * st.rstd * g.y + b.y,
+                                        (v[i].z - st.mean) * st.rstd * g.z + b.z, (v[i].w - st.mean) * st.rstd * g.w + b.w);
+    }
 }
 
 // d_patch[n*g*g + t-1] = bf16( ln_pre'(v)^T dx0[n*T + t] ), t >= 1
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ dx0, const float* __restrict__ v,
-                                                        const float* __restrict__ gamma, bf16* __restrict__ d_patch, int n,
-                                                        int T, int D) {
-    const int prow = blockIdx.x * 8 + (threadIdx.x >> 5);  // patch row
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads) embed_bwd_kernel(const float* __restrict__ dx0, const float* __restrict__ v,
+                                                                const float* __restrict__ gamma, bf16* __restrict__ d_patch,
+                                                                int n, int T) {
+    constexpr int D = NV * 128;
+    const int prow = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);  // patch row
     const int lane = threadIdx.x & 31;
     if (prow >= n * (T - 1)) return;
     const int nn = prow / (T - 1), t = prow % (T - 1) + 1;
     const size_t row = static_cast<size_t>(nn) * T + t;
-    const int nv = D >> 7;
     const float4* vr = reinterpret_cast<const float4*>(v + row * D);
     const float4* dr = reinterpret_cast<const float4*>(dx0 + row * D);
-    float4 xv[kMaxV], g[kMaxV];
+    float4 xv[NV], g[NV];
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) {
-            xv[i] = vr[i * 32 + lane];
-            g[i] = dr[i * 32 + lane];
-        }
-    ln_bwd_row(xv, g, gamma, nv, D, lane);
+    for (int i = 0; i < NV; ++i) {
+        xv[i] = vr[i * 32 + lane];
+        g[i] = dr[i * 32 + lane];
+    }
+    ln_bwd_row<NV>(xv, g, gamma, lane);
     uint2* out = reinterpret_cast<uint2*>(d_patch + static_cast<size_t>(prow) * D);
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i)
-        if (i < nv) out[i * 32 + lane] = pack4(g[i].x, g[i].y, g[i].z, g[i].w);
+    for (int i = 0; i < NV; ++i) out[i * 32 + lane] = pack4(g[i].x, g[i].y, g[i].z, g[i].w);
 }
+
+// launch KERNEL<NV>(args...) for the supported widths D = 128 * NV
+#define PCG_DISPATCH_NV(D, KERNEL, GRID, STREAM, ...)                                                        \
+    switch ((D) >> 7) {                                                                                      \
+        case 1: KERNEL<1><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
+        case 2: KERNEL<2><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
+        case 4: KERNEL<4><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
+        case 6: KERNEL<6><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
+        case 8: KERNEL<8><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
+        case 10: KERNEL<10><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        case 12: KERNEL<12><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        default: return ::pcg::set_error(-1, "width %d is not one of 128*{1,2,4,6,8,10,12}", (D));           \
+    }
 
 // --------------------------------------------------------------------------------------------------------
 // head: one CTA per cutout.
@@ -352,8 +366,8 @@ extern "C" int pcg_layernorm_fwd(const float* x, const float* gamma, const float
     PCG_CHECK_ARG(x && gamma && beta && y_bf16 && rows > 0, "pcg_layernorm_fwd: bad arguments");
     if (int rc = check_d("pcg_layernorm_fwd", D)) return rc;
     ProfileScope prof(PCG_PROF_LAYERNORM, 6.0 * rows * D, static_cast<cudaStream_t>(stream));
-    layernorm_fwd_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, gamma, beta, static_cast<bf16*>(y_bf16), rows, D);
+    PCG_DISPATCH_NV(D, layernorm_fwd_kernel, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream), x, gamma, beta,
+                    static_cast<bf16*>(y_bf16), rows);
     PCG_LAUNCH_CHECK("layernorm_fwd_kernel");
     return 0;
 }
@@ -363,8 +377,8 @@ extern "C" int pcg_layernorm_bwd(const void* dy_bf16, const float* x, const floa
     PCG_CHECK_ARG(dy_bf16 && x && gamma && dx_io && dx_bf16 && rows > 0, "pcg_layernorm_bwd: bad arguments");
     if (int rc = check_d("pcg_layernorm_bwd", D)) return rc;
     ProfileScope prof(PCG_PROF_LAYERNORM, 16.0 * rows * D, static_cast<cudaStream_t>(stream));
-    layernorm_bwd_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows, D);
+    PCG_DISPATCH_NV(D, layernorm_bwd_kernel, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream),
+                    static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows);
     PCG_LAUNCH_CHECK("layernorm_bwd_kernel");
     return 0;
 }
@@ -374,8 +388,8 @@ extern "C" int pcg_embed_fwd(const float* patch_out, const float* cls, const flo
     PCG_CHECK_ARG(patch_out && cls && pos && gamma && beta && v && x0 && n > 0 && T > 1, "pcg_embed_fwd: bad arguments");
     if (int rc = check_d("pcg_embed_fwd", D)) return rc;
     ProfileScope prof(PCG_PROF_EMBED, 12.0 * n * T * D, static_cast<cudaStream_t>(stream));
-    embed_fwd_kernel<<<ceil_div(n * T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(patch_out, cls, pos, gamma, beta,
-                                                                                          v, x0, n, T, D);
+    PCG_DISPATCH_NV(D, embed_fwd_kernel, ceil_div(n * T, kRowsPerBlock), static_cast<cudaStream_t>(stream), patch_out, cls,
+                    pos, gamma, beta, v, x0, n, T);
     PCG_LAUNCH_CHECK("embed_fwd_kernel");
     return 0;
 }
@@ -385,8 +399,8 @@ extern "C" int pcg_embed_bwd(const float* dx0, const float* v, const float* gamm
     PCG_CHECK_ARG(dx0 && v && gamma && d_patch_bf16 && n > 0 && T > 1, "pcg_embed_bwd: bad arguments");
     if (int rc = check_d("pcg_embed_bwd", D)) return rc;
     ProfileScope prof(PCG_PROF_EMBED, 10.0 * n * T * D, static_cast<cudaStream_t>(stream));
-    embed_bwd_kernel<<<ceil_div(n * (T - 1), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        dx0, v, gamma, static_cast<bf16*>(d_patch_bf16), n, T, D);
+    PCG_DISPATCH_NV(D, embed_bwd_kernel, ceil_div(n * (T - 1), kRowsPerBlock), static_cast<cudaStream_t>(stream), dx0, v,
+                    gamma, static_cast<bf16*>(d_patch_bf16), n, T);
     PCG_LAUNCH_CHECK("embed_bwd_kernel");
     return 0;
 }
