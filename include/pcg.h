@@ -30,9 +30,9 @@ enum { PCG_ACT_QUICKGELU = 0, PCG_ACT_GELU = 1 };
 /* GEMM epilogues (C = A[M,K] * B[N,K]^T, bf16 inputs, fp32 accumulation in tensor memory). */
 enum {
     PCG_GEMM_BF16 = 0,     /* out(bf16) = acc (+ bias)                                     */
-    PCG_GEMM_BIAS_ACT = 1, /* out(bf16) = h = acc + bias ; out2(bf16) = act(h)             */
+    PCG_GEMM_BIAS_ACT = 1, /* h = acc + bias ; out(bf16) = act'(h) ; out2(bf16) = act(h)   */
     PCG_GEMM_RESID_F32 = 2,/* out(f32)  = aux(f32 residual) + acc + bias                   */
-    PCG_GEMM_DACT = 3,     /* out(bf16) = acc * act'(aux(bf16 pre-activation))             */
+    PCG_GEMM_DACT = 3,     /* out(bf16) = acc * aux(bf16: the act'(h) stored by BIAS_ACT)  */
     PCG_GEMM_F32 = 4       /* out(f32)  = acc (+ bias)                                     */
 };
 

@@ -77,7 +77,7 @@ struct LayerStash {
     uint16_t* qkv; // [M,3D]
     uint16_t* o;   // [M,D]
     float* lse;    // [n*heads*T]
-    uint16_t* h;   // [M,4D] MLP pre-activation
+    uint16_t* h;   // [M,4D] act'(pre-activation) of the MLP (the derivative is stored, not h)
 };
 
 struct Stash {

@@ -61,22 +61,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 // QuickGELU x * sigmoid(1.702 x) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5: one MUFU.TANH + 3 FMA-class ops.
 // The activation is a template parameter so that erff never bloats the QuickGELU kernels' instruction footprint.
+// Returns act(h) and writes act'(h): the forward epilogue stores the DERIVATIVE (not the pre-activation) for the
+// backward pass, which then only multiplies (dgrad-only backward never needs h itself).
 template <int ACT>
-__device__ __forceinline__ float act_fwd(float h) {
+__device__ __forceinline__ float act_and_grad(float h, float& grad) {
     if constexpr (ACT == PCG_ACT_QUICKGELU) {
-        const float hh = 0.5f * h;
-        return fmaf(hh, tanh_approx(0.851f * h), hh);
+        const float s = fmaf(0.5f, tanh_approx(0.851f * h), 0.5f);  // sigmoid(1.702 h)
+        grad = s * fmaf(1.702f * h, 1.0f - s, 1.0f);
+        return h * s;
     } else {
-        return 0.5f * h * (1.0f + erff(h * 0.70710678118654752f));
-    }
-}
-template <int ACT>
-__device__ __forceinline__ float act_bwd(float h) {
-    if constexpr (ACT == PCG_ACT_QUICKGELU) {
-        const float s = fmaf(0.5f, tanh_approx(0.851f * h), 0.5f);
-        return s * fmaf(1.702f * h, 1.0f - s, 1.0f);
-    } else {
-        return 0.5f * (1.0f + erff(h * 0.70710678118654752f)) + h * 0.3989422804014327f * __expf(-0.5f * h * h);
+        const float cdf = 0.5f * (1.0f + erff(h * 0.70710678118654752f));
+        grad = cdf + h * 0.3989422804014327f * __expf(-0.5f * h * h);
+        return h * cdf;
     }
 }
 
@@ -268,11 +264,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) =
                                 make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
                         } else if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
+                            float4 g;
+                            const float4 a = make_float4(act_and_grad<ACT>(v.x, g.x), act_and_grad<ACT>(v.y, g.y),
+                                                         act_and_grad<ACT>(v.z, g.z), act_and_grad<ACT>(v.w, g.w));
                             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) =
-                                make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                                make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
                             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out2) + off) =
-                                make_uint2(pack_bf16(act_fwd<ACT>(v.x), act_fwd<ACT>(v.y)),
-                                           pack_bf16(act_fwd<ACT>(v.z), act_fwd<ACT>(v.w)));
+                                make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
                         } else if constexpr (MODE == PCG_GEMM_RESID_F32) {
                             *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) =
                                 make_float4(__uint_as_float(ax[0]) + v.x, __uint_as_float(ax[1]) + v.y,
@@ -280,9 +278,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         } else if constexpr (MODE == PCG_GEMM_DACT) {
                             const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&ax[0]);
                             const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&ax[1]);
-                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) = make_uint2(
-                                pack_bf16(v.x * act_bwd<ACT>(__low2float(h01)), v.y * act_bwd<ACT>(__high2float(h01))),
-                                pack_bf16(v.z * act_bwd<ACT>(__low2float(h23)), v.w * act_bwd<ACT>(__high2float(h23))));
+                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) =
+                                make_uint2(pack_bf16(v.x * __low2float(h01), v.y * __high2float(h01)),
+                                           pack_bf16(v.z * __low2float(h23), v.w * __high2float(h23)));
                         } else {  // PCG_GEMM_F32
                             *reinterpret_cast<float4*>(static_cast<float*>(p.out) + off) = v;
                         }
@@ -385,7 +383,7 @@ int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
 }
 template <int BN, int MODE>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
-    if constexpr (MODE == PCG_GEMM_BIAS_ACT || MODE == PCG_GEMM_DACT) {
+    if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
         if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU>(ma, mb, p, stream);
     }
     return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU>(ma, mb, p, stream);

@@ -69,23 +69,20 @@ def test_gemm_epilogues(cuda_device, m, n, k, act):
     bias = torch.randn(n, generator=g).to(cuda_device)
     acc = a.float() @ b.float().t()
     f = quick_gelu if act == native.ACT_QUICKGELU else torch.nn.functional.gelu
-    # bias + activation
-    h, act_out = ops.gemm(native.GEMM_BIAS_ACT, a, b, bias=bias, act=act)
-    check_close(h, acc + bias, 4e-3, "bias_act: pre-activation")
+    # bias + activation: the kernel stores act'(h) (for the backward multiply) and act(h)
+    hx = (acc + bias).clone().requires_grad_()
+    want_grad = torch.autograd.grad(f(hx).sum(), hx)[0]
+    dact_out, act_out = ops.gemm(native.GEMM_BIAS_ACT, a, b, bias=bias, act=act)
+    check_close(dact_out, want_grad, 6e-3, "bias_act: stored derivative")
     check_close(act_out, f(acc + bias), 6e-3, "bias_act: activation")
     # residual
     res = torch.randn(m, n, generator=g).to(cuda_device)
     out = ops.gemm(native.GEMM_RESID_F32, a, b, bias=bias, aux=res)
     check_close(out, res + acc + bias, 2e-5, "residual f32")
-    # activation derivative
-    hpre = torch.randn(m, n, generator=g).to(cuda_device, bf16)
-    if act == native.ACT_QUICKGELU:
-        dact = dquick_gelu(hpre.float())
-    else:
-        x = hpre.float().requires_grad_()
-        dact = torch.autograd.grad(torch.nn.functional.gelu(x).sum(), x)[0]
-    out = ops.gemm(native.GEMM_DACT, a, b, aux=hpre, act=act)
-    check_close(out, acc * dact, 6e-3, "dact")
+    # multiply by the stored activation derivative
+    dact = torch.randn(m, n, generator=g).to(cuda_device, bf16)
+    out = ops.gemm(native.GEMM_DACT, a, b, aux=dact, act=act)
+    check_close(out, acc * dact.float(), 4e-3, "dact")
 
 
 def test_gemm_strided_operand(cuda_device):
