@@ -140,6 +140,67 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         : "memory");
 }
 
+// TMEM load of W (16 or 32) consecutive columns of this warp's 32 lanes
+template <int W>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[W]) {
+    static_assert(W == 16 || W == 32, "tmem_ld: W must be 16 or 32");
+    if constexpr (W == 32)
+        tmem_ld_32x32(taddr, r);
+    else
+        tmem_ld_32x16(taddr, r);
+}
+
+// registers -> TMEM: 32 lanes x {8, 16} consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+template <int W>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[W]) {
+    static_assert(W == 8 || W == 16, "tmem_st: W must be 8 or 16");
+    if constexpr (W == 16)
+        tmem_st_32x16(taddr, r);
+    else
+        tmem_st_32x8(taddr, r);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is 128 lanes x (K/2) columns of packed bf16 pairs (low half = lower k).
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Same descriptor with a leading-dimension byte offset: for an MN-major operand wider than one 64-element swizzle
+// atom it is the distance between consecutive 64-element chunks along M / N.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// named barrier over `count` threads (count % 32 == 0); id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // 3-D tiled TMA load (inner, middle, outer coordinates).
 __device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
                                             int32_t c2, uint64_t cache_hint) {

@@ -159,10 +159,11 @@ def attn_reference(qkv, n, t, heads):
 
 @pytest.mark.parametrize("n,t,heads", [(2, 50, 12), (1, 197, 12), (3, 257, 16), (1, 577, 16), (2, 17, 2), (1, 64, 2),
                                        (1, 65, 2), (2, 128, 1), (2, 256, 4), (1, 272, 2), (1, 130, 2), (2, 192, 3),
-                                       (5, 257, 3), (1, 200, 1)])
+                                       (5, 257, 3), (1, 200, 1), (1, 66, 1), (1, 129, 2), (2, 145, 2), (1, 241, 1),
+                                       (2, 113, 2)])
 @pytest.mark.parametrize("tc", [0, 1])
 def test_attention(cuda_device, n, t, heads, tc):
-    """tc=1 routes 128 <= T <= 272 through the tcgen05 kernels, tc=0 through the mma.sync kernels."""
+    """tc=1 routes 66 <= T <= 257 through the tcgen05 kernels (the default), tc=0 through the mma.sync kernels."""
     native.lib().pcg_attn_set_legacy(0 if tc else 1)
     d = heads * 64
     g = torch.Generator(device="cpu").manual_seed(t + heads)
@@ -177,7 +178,7 @@ def test_attention(cuda_device, n, t, heads, tc):
     d_out = torch.randn(n * t, d, generator=g).to(cuda_device, bf16)
     o_ref.backward(d_out.float())
     d_qkv = ops.attn_bwd(qkv, out, d_out, lse, n, t, heads)
-    native.lib().pcg_attn_set_legacy(1)
+    native.lib().pcg_attn_set_legacy(0)
     for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
         check_close(d_qkv[:, sl], ref.grad[:, sl], 1.5e-2, f"attention {name} T={t} tc={tc}")
 

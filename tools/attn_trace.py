@@ -1,0 +1,82 @@
+"""Phase timeline of the tcgen05 attention kernels: per-CTA clock64 stamps (pcg_attn_set_trace), median over CTAs.
+
+Also prints per-iteration device times so that outliers are visible."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from perceptor_b200 import native, ops  # noqa: E402
+
+FWD = {0: "start", 1: "setup done", 2: "K+Q landed", 3: "V landed", 4: "S ready (w0)", 5: "max pass done", 6: "exp pass done",
+       7: "O ready", 8: "epilogue done", 9: "edge row done", 10: "all warps done"}
+BWD = {0: "start", 1: "loads landed", 2: "edge prologue done", 3: "edge gemv done", 4: "b0 S/dP ready", 5: "b0 alu done",
+       6: "b1 S/dP ready", 7: "b1 alu done", 8: "b2 S/dP ready", 9: "b2 alu done", 10: "b3 S/dP ready", 11: "b3 alu done",
+       12: "tile0 mma done", 13: "tile1 mma done", 14: "epilogues done", 15: "all warps done", 16: "ctl b0 P/dS seen",
+       17: "ctl b1 P/dS seen", 18: "ctl b2 P/dS seen", 19: "ctl b3 P/dS seen"}
+
+
+def show(trace, names, title):
+    t = trace.cpu().double()
+    valid = t[:, 0] > 0
+    t = t[valid]
+    rel = t - t[:, :1]
+    print(f"--- {title}: {t.shape[0]} CTAs, cycles since CTA start (median / p90)")
+    order = sorted(names, key=lambda k: float(rel[:, k][t[:, k] > 0].median()) if (t[:, k] > 0).any() else 1e18)
+    for k in order:
+        m = t[:, k] > 0
+        if not m.any():
+            continue
+        v = rel[:, k][m]
+        print(f"  {names[k]:22s} {v.median():9.0f} {v.quantile(0.9):9.0f}   ({int(m.sum())} CTAs)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--t", type=int, default=257)
+    ap.add_argument("--heads", type=int, default=16)
+    ap.add_argument("--iters", type=int, default=8)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    n, t, h = args.n, args.t, args.heads
+    d = h * 64
+    qkv = torch.randn(n * t, 3 * d, device=dev)
+    qkv[:, :d] *= 0.125
+    qkv = qkv.to(torch.bfloat16)
+    d_out = torch.randn(n * t, d, device=dev).to(torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        out, lse = ops.attn_fwd(qkv, n, t, h)
+        ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
+    tf, tb = [], []
+    for _ in range(args.iters):
+        flush.zero_()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out, lse = ops.attn_fwd(qkv, n, t, h)
+        e[1].record()
+        ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
+        e[2].record()
+        torch.cuda.synchronize()
+        tf.append(e[0].elapsed_time(e[1]) * 1e3)
+        tb.append(e[1].elapsed_time(e[2]) * 1e3)
+    print("fwd us per iteration:", " ".join(f"{x:.0f}" for x in tf))
+    print("bwd us per iteration:", " ".join(f"{x:.0f}" for x in tb))
+    n_cta = 2 * h * n
+    trace = torch.zeros(n_cta, 32, dtype=torch.int64, device=dev)
+    native.lib().pcg_attn_set_trace(trace.data_ptr())
+    out, lse = ops.attn_fwd(qkv, n, t, h)
+    torch.cuda.synchronize()
+    show(trace, FWD, "forward")
+    trace.zero_()
+    ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
+    torch.cuda.synchronize()
+    native.lib().pcg_attn_set_trace(None)
+    show(trace[: h * n], BWD, "backward")
+
+
+if __name__ == "__main__":
+    main()
