@@ -162,9 +162,9 @@ __device__ __forceinline__ void mma_rows_t_x_cols(uint32_t tmem_d, const uint8_t
 }
 
 // phase stamps of one CTA for tools/attn_trace.py; a null check per stamp when tracing is off
-#define PCG_TRACE(slot)                                                       \
-    do {                                                                      \
-        if (p.trace != nullptr && lane == 0) p.trace[cta_id * 32 + (slot)] = clock64(); \
+#define PCG_TRACE(slot)                                                                   \
+    do {                                                                                  \
+        if (p.trace != nullptr && lane == 0) p.trace[cta_id * 32 + (slot)] = clock64();   \
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -173,10 +173,12 @@ __device__ __forceinline__ void mma_rows_t_x_cols(uint32_t tmem_d, const uint8_t
 constexpr int kFwdThreads = 192;  // warps 0-3 softmax (TMEM lane quarters), 4 TMA + MMA, 5 edge query row
 constexpr int kFwdOffV = 2 * kBlkBytes;
 constexpr int kFwdOffQ = 4 * kBlkBytes;
-constexpr int kFwdOffX = 5 * kBlkBytes;               // float k_x[64], v_x[64], q_x[64], p_x[256]
-constexpr int kFwdOffBar = kFwdOffX + 3 * 256 + 1024;  // 5 mbarriers + tmem slot
+constexpr int kFwdOffX = 5 * kBlkBytes;                // float k_x[64], v_x[64], q_x[64], p_x[256]
+constexpr int kFwdOffBar = kFwdOffX + 3 * 256 + 1024;  // 7 mbarriers + tmem slot
 constexpr int kFwdSmemBytes = kFwdOffBar + 64 + 1024;
-constexpr uint32_t kFwdColO = 128;
+// TMEM columns: S [0, nk).  P (packed bf16 pairs) overwrites consumed S columns: keys >= 128 first, into
+// [128, 192), then keys < 128 into [0, 64).  O accumulates in [192, 256), free once the first phase has read it.
+constexpr uint32_t kFwdColPHi = 128, kFwdColO = 192;
 
 struct FwdParams {
     int T, heads;
@@ -186,42 +188,83 @@ struct FwdParams {
     bf16* out;
     float* lse;
     long long* trace;  // optional [ctas][32] clock64 stamps (tools/attn_trace.py), nullptr in production
+    int stagger_ctas;    // the first wave: CTAs with a linear index below this ...
+    int stagger_cycles;  // ... are delayed by this much when they are the second to arrive on their SM
 };
 
-template <int W>
-__device__ __forceinline__ float fwd_chunk_max(uint32_t taddr, int c, int nv, float mx) {
-    uint32_t v[W];
-    tmem_ld<W>(taddr + c, v);
-    tmem_wait_ld();
-    if (c + W <= nv) {
+// Two forward CTAs share an SM so that one's softmax (MUFU) overlaps the other's MMAs.  Launched together they
+// run in lockstep and queue for the same unit at the same time; holding back every second arrival of the first
+// wave by about half a CTA lifetime puts the pairs in anti-phase, and the offset then carries through the grid.
+__device__ unsigned int g_fwd_sm_arrivals[1024];
+
+__device__ __forceinline__ float chunk_max32(const uint32_t (&v)[32], int c, int nv, float mx) {
+    float m0 = mx, m1 = -INFINITY;
+    if (c + 32 <= nv) {
 #pragma unroll
-        for (int j = 0; j < W; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; j += 2) {
+            m0 = fmaxf(m0, __uint_as_float(v[j]));
+            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < W; ++j) mx = fmaxf(mx, (c + j < nv) ? __uint_as_float(v[j]) : -INFINITY);
+        for (int j = 0; j < 32; j += 2) {
+            m0 = fmaxf(m0, (c + j < nv) ? __uint_as_float(v[j]) : -INFINITY);
+            m1 = fmaxf(m1, (c + j + 1 < nv) ? __uint_as_float(v[j + 1]) : -INFINITY);
+        }
+    }
+    return fmaxf(m0, m1);
+}
+// row max over S columns [0, c_end), c_end a multiple of 32 (columns >= nv are masked, whatever they hold);
+// the load of chunk c + 32 is in flight while chunk c is reduced
+__device__ __forceinline__ float fwd_row_max(uint32_t trow, int c_end, int nv, float mx) {
+    uint32_t va[32], vb[32];
+    tmem_ld<32>(trow, va);
+    for (int c = 0; c < c_end; c += 64) {
+        tmem_wait_ld();
+        if (c + 32 < c_end) tmem_ld<32>(trow + c + 32, vb);
+        mx = chunk_max32(va, c, nv, mx);
+        if (c + 32 < c_end) {
+            tmem_wait_ld();
+            if (c + 64 < c_end) tmem_ld<32>(trow + c + 64, va);
+            mx = chunk_max32(vb, c + 32, nv, mx);
+        }
     }
     return mx;
 }
-// P = exp2(S log2e - mb) for W columns, written back over the (already consumed) S columns as packed bf16
-template <int W>
-__device__ __forceinline__ float fwd_chunk_exp(uint32_t taddr, int c, int nv, float mb, float sum) {
-    uint32_t v[W];
-    tmem_ld<W>(taddr + c, v);
-    tmem_wait_ld();
-    uint32_t pk[W / 2];
-    const bool full = c + W <= nv;
+__device__ __forceinline__ float chunk_exp32(const uint32_t (&v)[32], int c, int nv, float mb, uint32_t tdst, float sum) {
+    uint32_t pk[16];
+    const bool full = c + 32 <= nv;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < W / 2; ++j) {
+    for (int j = 0; j < 16; ++j) {
         float e0 = exp2f(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mb));
         float e1 = exp2f(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mb));
         if (!full) {
             e0 = (c + 2 * j < nv) ? e0 : 0.f;
             e1 = (c + 2 * j + 1 < nv) ? e1 : 0.f;
         }
-        sum += e0 + e1;
+        s0 += e0;
+        s1 += e1;
         pk[j] = pack_bf16(e0, e1);
     }
-    tmem_st<W / 2>(taddr + (c >> 1), pk);
+    tmem_st<16>(tdst, pk);
+    return sum + (s0 + s1);
+}
+// P = exp2(S log2e - mb) for S columns [c_begin, c_end) -> packed bf16 at TMEM columns p_col + (c - c_begin) / 2
+__device__ __forceinline__ float fwd_row_exp(uint32_t trow, int c_begin, int c_end, uint32_t p_col, int nv, float mb,
+                                             float sum) {
+    uint32_t va[32], vb[32];
+    tmem_ld<32>(trow + c_begin, va);
+    for (int c = c_begin; c < c_end; c += 64) {
+        tmem_wait_ld();
+        if (c + 32 < c_end) tmem_ld<32>(trow + c + 32, vb);
+        sum = chunk_exp32(va, c, nv, mb, trow + p_col + ((c - c_begin) >> 1), sum);
+        if (c + 32 < c_end) {
+            tmem_wait_ld();
+            if (c + 64 < c_end) tmem_ld<32>(trow + c + 64, va);
+            sum = chunk_exp32(vb, c + 32, nv, mb, trow + p_col + ((c + 32 - c_begin) >> 1), sum);
+        }
+    }
     return sum;
 }
 
@@ -237,8 +280,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
     float* vx = kx + 64;
     float* qx = kx + 128;
     float* pbuf = kx + 192;  // [256] the edge row's probabilities
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kFwdOffBar);  // 0 K+Q, 1 V, 2 S, 3 P, 4 O
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    // mbarriers: 0 K+Q landed, 1 V landed, 2 S ready, 3 P(keys >= 128) stored, 4 P(keys < 128) stored, 5 O ready,
+    // 6 edge rows in shared memory
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kFwdOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -247,25 +292,45 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
     const bool has_edge_row = (q0 + 128 >= nv);  // the CTA of the last tile also computes query row x
     const size_t cta_id = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     if (warp == 0) PCG_TRACE(0);
-    const bf16* xrow_g = p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd;
 
+    uint32_t xq = 0, xk = 0, xv = 0;
     if (warp == 4) {
         if (lane == 0) {
             mbar_init(&bars[0], 1);
             mbar_init(&bars[1], 1);
             mbar_init(&bars[2], 1);
             mbar_init(&bars[3], 4);
-            mbar_init(&bars[4], 1);
+            mbar_init(&bars[4], 4);
+            mbar_init(&bars[5], 1);
+            mbar_init(&bars[6], 1);
             fence_barrier_init();
-            tma_prefetch_desc(&map_qkv);
+            if (cta_id < static_cast<size_t>(p.stagger_ctas)) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                if (atomicAdd(&g_fwd_sm_arrivals[smid & 1023], 1u) & 1u) {
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < p.stagger_cycles) {
+                    }
+                }
+            }
+            // the loads only need the barriers: start them before the TMEM allocation and the CTA-wide sync
+            const int nblk = (nk + 127) >> 7;
+            mbar_arrive_expect_tx(&bars[0], (nblk + 1) * kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[0], sm_q, h * kHd, q0, n, kEvictFirst);
+            for (int i = 0; i < nblk; ++i)
+                tma_load_3d(&map_qkv, &bars[0], sm_k + i * kBlkBytes, D + h * kHd, i * 128, n, kEvictNormal);
+            mbar_arrive_expect_tx(&bars[1], nblk * kBlkBytes);
+            for (int i = 0; i < nblk; ++i)
+                tma_load_3d(&map_qkv, &bars[1], sm_v + i * kBlkBytes, 2 * D + h * kHd, i * 128, n, kEvictNormal);
         }
         __syncwarp();
         tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     } else if (warp == 5) {
-        load_row_f32(qx, xrow_g, lane);
-        load_row_f32(kx, xrow_g + D, lane);
-        load_row_f32(vx, xrow_g + 2 * D, lane);
+        const bf16* xrow_g = p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd + 2 * lane;
+        xq = *reinterpret_cast<const uint32_t*>(xrow_g);
+        xk = *reinterpret_cast<const uint32_t*>(xrow_g + D);
+        xv = *reinterpret_cast<const uint32_t*>(xrow_g + 2 * D);
     }
     tc_fence_before();
     __syncthreads();
@@ -275,14 +340,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
 
     if (warp == 4) {
         if (lane == 0) {
-            const int nblk = (nk + 127) >> 7;
-            mbar_arrive_expect_tx(&bars[0], (nblk + 1) * kBlkBytes);
-            tma_load_3d(&map_qkv, &bars[0], sm_q, h * kHd, q0, n, kEvictFirst);
-            for (int i = 0; i < nblk; ++i)
-                tma_load_3d(&map_qkv, &bars[0], sm_k + i * kBlkBytes, D + h * kHd, i * 128, n, kEvictNormal);
-            mbar_arrive_expect_tx(&bars[1], nblk * kBlkBytes);
-            for (int i = 0; i < nblk; ++i)
-                tma_load_3d(&map_qkv, &bars[1], sm_v + i * kBlkBytes, 2 * D + h * kHd, i * 128, n, kEvictNormal);
             mbar_wait(&bars[0], 0);
             PCG_TRACE(2);
             tc_fence_after();
@@ -290,65 +347,73 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
             umma_commit(&bars[2]);
             mbar_wait(&bars[1], 0);  // V landed
             PCG_TRACE(3);
-            mbar_wait(&bars[3], 0);  // P is in TMEM
-            tc_fence_after();
+            // O = P V with A = P from TMEM (8 columns of bf16 pairs per 16 keys), keys >= 128 first
             const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
             const int ksteps = nk >> 4;
-            for (int ks = 0; ks < ksteps; ++ks)  // O = P V, A = P from TMEM (8 columns of bf16 pairs per step)
+            if (ksteps > 8) {
+                mbar_wait(&bars[3], 0);
+                tc_fence_after();
+                for (int ks = 8; ks < ksteps; ++ks)
+                    umma_f16_ts(tmem + kFwdColO, tmem + kFwdColPHi + (ks - 8) * 8,
+                                umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)), idesc, ks != 8);
+            }
+            mbar_wait(&bars[4], 0);
+            tc_fence_after();
+            for (int ks = 0; ks < min(ksteps, 8); ++ks)
                 umma_f16_ts(tmem + kFwdColO, tmem + ks * 8, umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)), idesc,
-                            ks != 0);
-            umma_commit(&bars[4]);
+                            ksteps > 8 || ks != 0);
+            umma_commit(&bars[5]);
         }
     } else if (warp < 4) {
         const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
         const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        mbar_wait(&bars[6], 0);
         mbar_wait(&bars[0], 0);
         const float sx = row_dot(sm_q, r, kx);  // score against the edge key, while the MMA runs
         mbar_wait(&bars[2], 0);
         tc_fence_after();
         if (warp == 0) PCG_TRACE(4);
-        float mx = sx;
-        int c = 0;
-        for (; c + 32 <= nk; c += 32) mx = fwd_chunk_max<32>(trow, c, nv, mx);
-        if (c < nk) mx = fwd_chunk_max<16>(trow, c, nv, mx);
+        const int nk32 = (nk + 31) & ~31;
+        const float mx = fwd_row_max(trow, nk32, nv, sx);
         const float mb = mx * kLog2e;
-        float sum = 0.f;
         if (warp == 0) PCG_TRACE(5);
-        for (c = 0; c + 32 <= nk; c += 32) sum = fwd_chunk_exp<32>(trow, c, nv, mb, sum);
-        if (c < nk) sum = fwd_chunk_exp<16>(trow, c, nv, mb, sum);
-        const float px = exp2f(fmaf(sx, kLog2e, -mb));
-        sum += px;
+        float sum = 0.f;
+        if (nk32 > 128) sum = fwd_row_exp(trow, 128, nk32, kFwdColPHi, nv, mb, sum);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[3]);
+        sum = fwd_row_exp(trow, 0, min(nk32, 128), 0, nv, mb, sum);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[4]);
         if (warp == 0) PCG_TRACE(6);
+        const float px = exp2f(fmaf(sx, kLog2e, -mb));
+        sum += px;
         if (q0 + r < nv) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + q0 + r] = mx + logf(sum);
         const float inv = 1.0f / sum;
-        mbar_wait(&bars[4], 0);
+        mbar_wait(&bars[5], 0);
         tc_fence_after();
         if (warp == 0) PCG_TRACE(7);
         // O row: (P V + p_x v_x) / sum -> bf16 through the (now free) Q tile, then coalesced 16-byte stores
+        uint32_t v[64];
+        tmem_ld_32x32(trow + kFwdColO, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+        tmem_ld_32x32(trow + kFwdColO + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
+        tmem_wait_ld();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld<32>(trow + kFwdColO + half * 32, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const float4 xa = *reinterpret_cast<const float4*>(vx + half * 32 + g * 8);
-                const float4 xb = *reinterpret_cast<const float4*>(vx + half * 32 + g * 8 + 4);
-                const uint4 o = make_uint4(
-                    pack_bf16(fmaf(px, xa.x, __uint_as_float(v[8 * g])) * inv,
-                              fmaf(px, xa.y, __uint_as_float(v[8 * g + 1])) * inv),
-                    pack_bf16(fmaf(px, xa.z, __uint_as_float(v[8 * g + 2])) * inv,
-                              fmaf(px, xa.w, __uint_as_float(v[8 * g + 3])) * inv),
-                    pack_bf16(fmaf(px, xb.x, __uint_as_float(v[8 * g + 4])) * inv,
-                              fmaf(px, xb.y, __uint_as_float(v[8 * g + 5])) * inv),
-                    pack_bf16(fmaf(px, xb.z, __uint_as_float(v[8 * g + 6])) * inv,
-                              fmaf(px, xb.w, __uint_as_float(v[8 * g + 7])) * inv));
-                *reinterpret_cast<uint4*>(sm_q + row_chunk(r, half * 4 + g)) = o;
-            }
+        for (int g = 0; g < 8; ++g) {
+            const float4 xa = *reinterpret_cast<const float4*>(vx + g * 8);
+            const float4 xb = *reinterpret_cast<const float4*>(vx + g * 8 + 4);
+            const uint4 o = make_uint4(pack_bf16(fmaf(px, xa.x, __uint_as_float(v[8 * g])) * inv,
+                                                 fmaf(px, xa.y, __uint_as_float(v[8 * g + 1])) * inv),
+                                       pack_bf16(fmaf(px, xa.z, __uint_as_float(v[8 * g + 2])) * inv,
+                                                 fmaf(px, xa.w, __uint_as_float(v[8 * g + 3])) * inv),
+                                       pack_bf16(fmaf(px, xb.x, __uint_as_float(v[8 * g + 4])) * inv,
+                                                 fmaf(px, xb.y, __uint_as_float(v[8 * g + 5])) * inv),
+                                       pack_bf16(fmaf(px, xb.z, __uint_as_float(v[8 * g + 6])) * inv,
+                                                 fmaf(px, xb.w, __uint_as_float(v[8 * g + 7])) * inv));
+            *reinterpret_cast<uint4*>(sm_q + row_chunk(r, g)) = o;
         }
         __syncwarp();
         bf16* gout = p.out + static_cast<size_t>(n) * p.T * D + h * kHd;
@@ -360,38 +425,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
                     *reinterpret_cast<const uint4*>(sm_q + row_chunk(row, ch));
         }
         if (warp == 0) PCG_TRACE(8);
-    } else if (has_edge_row) {
-        // query row x against every key, on the CUDA cores: lane owns keys lane + 32 jj
-        mbar_wait(&bars[0], 0);
-        float s[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = lane + 32 * jj;
-            s[jj] = (j < nv) ? row_dot(sm_k, j, qx) : -INFINITY;
-        }
-        float sxx = 0.f;
-#pragma unroll
-        for (int d = 0; d < 64; ++d) sxx = fmaf(qx[d], kx[d], sxx);
-        float mx = sxx;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) mx = fmaxf(mx, s[jj]);
-        mx = warp_max(mx);
-        const float mb = mx * kLog2e;
-        float part = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            s[jj] = exp2f(fmaf(s[jj], kLog2e, -mb));
-            part += s[jj];
-        }
-        const float exx = exp2f(fmaf(sxx, kLog2e, -mb));
-        const float sum = warp_sum(part) + exx;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) pbuf[lane + 32 * jj] = s[jj];
+    } else {
+        // edge token rows as float vectors for everyone (loaded into registers before the CTA-wide sync)
+        qx[2 * lane] = bf_lo(xq), qx[2 * lane + 1] = bf_hi(xq);
+        kx[2 * lane] = bf_lo(xk), kx[2 * lane + 1] = bf_hi(xk);
+        vx[2 * lane] = bf_lo(xv), vx[2 * lane + 1] = bf_hi(xv);
         __syncwarp();
-        mbar_wait(&bars[1], 0);
-        edge_gemv(pbuf, sm_v, nv, exx, vx, p.out + (static_cast<size_t>(n) * p.T + nv) * D + h * kHd, 1.0f / sum, lane);
-        if (lane == 0) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + nv] = mx + logf(sum);
-        PCG_TRACE(9);
+        if (lane == 0) mbar_arrive(&bars[6]);
+        if (has_edge_row) {
+            // query row x against every key, on the CUDA cores: lane owns keys lane + 32 jj
+            mbar_wait(&bars[0], 0);
+            float s[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = lane + 32 * jj;
+                s[jj] = (j < nv) ? row_dot(sm_k, j, qx) : -INFINITY;
+            }
+            float sxx = 0.f;
+#pragma unroll
+            for (int d = 0; d < 64; ++d) sxx = fmaf(qx[d], kx[d], sxx);
+            float mx = sxx;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) mx = fmaxf(mx, s[jj]);
+            mx = warp_max(mx);
+            const float mb = mx * kLog2e;
+            float part = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                s[jj] = exp2f(fmaf(s[jj], kLog2e, -mb));
+                part += s[jj];
+                pbuf[lane + 32 * jj] = s[jj];
+            }
+            const float exx = exp2f(fmaf(sxx, kLog2e, -mb));
+            const float sum = warp_sum(part) + exx;
+            __syncwarp();
+            mbar_wait(&bars[1], 0);
+            edge_gemv(pbuf, sm_v, nv, exx, vx, p.out + (static_cast<size_t>(n) * p.T + nv) * D + h * kHd, 1.0f / sum,
+                      lane);
+            if (lane == 0) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + nv] = mx + logf(sum);
+            PCG_TRACE(9);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -402,16 +475,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
 // ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kBwdThreads = 384;  // warps 0-7 elementwise (lane quarter = warp & 3, column half = warp >> 2),
-                                  // warp 8 TMA + MMA, warps 9-11 edge rows (dV_x, dK_x, dQ_x)
+constexpr int kBwdThreads = 384;  // warps 0-7 elementwise (lane quarter = warp & 3, column phase = warp >> 2),
+                                  // warp 8 TMA + MMA, warps 9-11 edge token (row x and column x of the scores)
 constexpr int kBwdOffQ = 0;
 constexpr int kBwdOffK = 2 * kBlkBytes;
 constexpr int kBwdOffV = 4 * kBlkBytes;
 constexpr int kBwdOffDO = 6 * kBlkBytes;
-constexpr int kBwdOffPT = 8 * kBlkBytes;    // P^T  [128 keys x 128 queries] bf16, two 64-column blocks
-constexpr int kBwdOffDST = 10 * kBlkBytes;  // dS^T, same layout
+constexpr int kBwdOffPT = 8 * kBlkBytes;      // P^T  [128 keys x 128 queries] bf16, two 64-column blocks
+constexpr int kBwdOffDST = 10 * kBlkBytes;    // dS^T, same layout
 constexpr int kBwdOffStage = 12 * kBlkBytes;  // 8 warps x [32 rows x 64 B] epilogue staging
-constexpr int kBwdOffVec = 13 * kBlkBytes;  // float[256] x 6: lse2, delta, pcol, dscol, prow, dsrow
+constexpr int kBwdOffVec = 13 * kBlkBytes;    // float[256] x 6: lse2, delta, pcol, dscol, prow, dsrow
 constexpr int kBwdOffX = kBwdOffVec + 6 * 1024;  // float[64] x 4: q_x, k_x, v_x, dO_x; then 8 scalars
 constexpr int kBwdOffBar = kBwdOffX + 4 * 256 + 32;
 constexpr int kBwdSmemBytes = kBwdOffBar + 64 + 1024;
@@ -422,27 +495,27 @@ struct BwdParams {
     int nv;       // T - 1
     int n_tiles;  // ceil(nv / 128): 1 or 2
     const bf16* qkv;
+    const bf16* out;
     const bf16* d_out;
     const float* lse;
-    const float* delta;
     bf16* d_qkv;
     long long* trace;
 };
 
-// W columns of one block: P^T and dS^T for this thread's key row, written as bf16 into the swizzled smem blocks
-template <int W>
-__device__ __forceinline__ void bwd_chunk(uint32_t t_s, uint32_t t_dp, int c, const float* lse2, const float* delta,
-                                          bool row_ok, uint8_t* pt_blk, uint8_t* dst_blk, int r) {
-    uint32_t s[W], dp[W];
-    tmem_ld<W>(t_s + c, s);
-    tmem_ld<W>(t_dp + c, dp);
-    tmem_wait_ld();
+// 16 columns of one block for this thread's key row: P^T = exp2(S^T log2e - lse2), dS^T = P^T (dP^T - delta) as
+// packed bf16 (two 16-byte chunks each) ...
+struct Cols16 {
+    uint4 p[2], ds[2];
+};
+__device__ __forceinline__ Cols16 bwd_cols16(const uint32_t (&s)[16], const uint32_t (&dp)[16], const float* lse2,
+                                             const float* delta, bool row_ok) {
+    Cols16 o;
 #pragma unroll
-    for (int g = 0; g < W / 8; ++g) {
-        const float4 la = *reinterpret_cast<const float4*>(lse2 + c + 8 * g);
-        const float4 lb = *reinterpret_cast<const float4*>(lse2 + c + 8 * g + 4);
-        const float4 da = *reinterpret_cast<const float4*>(delta + c + 8 * g);
-        const float4 db = *reinterpret_cast<const float4*>(delta + c + 8 * g + 4);
+    for (int g = 0; g < 2; ++g) {
+        const float4 la = *reinterpret_cast<const float4*>(lse2 + 8 * g);
+        const float4 lb = *reinterpret_cast<const float4*>(lse2 + 8 * g + 4);
+        const float4 da = *reinterpret_cast<const float4*>(delta + 8 * g);
+        const float4 db = *reinterpret_cast<const float4*>(delta + 8 * g + 4);
         const float l[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
         const float d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
         float pv[8], dsv[8];
@@ -451,14 +524,21 @@ __device__ __forceinline__ void bwd_chunk(uint32_t t_s, uint32_t t_dp, int c, co
             pv[k] = exp2f(fmaf(__uint_as_float(s[8 * g + k]), kLog2e, -l[k]));
             dsv[k] = pv[k] * (__uint_as_float(dp[8 * g + k]) - d[k]);
         }
-        uint4 pq = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
-                              pack_bf16(pv[6], pv[7]));
-        uint4 dq = make_uint4(pack_bf16(dsv[0], dsv[1]), pack_bf16(dsv[2], dsv[3]), pack_bf16(dsv[4], dsv[5]),
-                              pack_bf16(dsv[6], dsv[7]));
-        if (!row_ok) pq = dq = make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t off = row_chunk(r, ((c & 63) >> 3) + g);
-        *reinterpret_cast<uint4*>(pt_blk + off) = pq;
-        *reinterpret_cast<uint4*>(dst_blk + off) = dq;
+        o.p[g] = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                            pack_bf16(pv[6], pv[7]));
+        o.ds[g] = make_uint4(pack_bf16(dsv[0], dsv[1]), pack_bf16(dsv[2], dsv[3]), pack_bf16(dsv[4], dsv[5]),
+                             pack_bf16(dsv[6], dsv[7]));
+        if (!row_ok) o.p[g] = o.ds[g] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return o;
+}
+// ... and their stores into the swizzled [128 x 64] shared-memory blocks (16-byte chunks chunk0, chunk0 + 1 of row r)
+__device__ __forceinline__ void bwd_store16(const Cols16& o, uint8_t* pt_blk, uint8_t* dst_blk, int r, int chunk0) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const uint32_t off = row_chunk(r, chunk0 + g);
+        *reinterpret_cast<uint4*>(pt_blk + off) = o.p[g];
+        *reinterpret_cast<uint4*>(dst_blk + off) = o.ds[g];
     }
 }
 
@@ -494,6 +574,18 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t taddr, float coef, const f
     __syncwarp();
 }
 
+// partial sum_d a[d] * b[d] over one 16-byte chunk (8 bf16) of two rows
+__device__ __forceinline__ float chunk_dot(const uint4& x, const uint4& y) {
+    float acc0 = bf_lo(x.x) * bf_lo(y.x), acc1 = bf_hi(x.x) * bf_hi(y.x);
+    acc0 = fmaf(bf_lo(x.y), bf_lo(y.y), acc0);
+    acc1 = fmaf(bf_hi(x.y), bf_hi(y.y), acc1);
+    acc0 = fmaf(bf_lo(x.z), bf_lo(y.z), acc0);
+    acc1 = fmaf(bf_hi(x.z), bf_hi(y.z), acc1);
+    acc0 = fmaf(bf_lo(x.w), bf_lo(y.w), acc0);
+    acc1 = fmaf(bf_hi(x.w), bf_hi(y.w), acc1);
+    return acc0 + acc1;
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                    const BwdParams p) {
@@ -506,37 +598,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     uint8_t* sm_do = sm + kBwdOffDO;
     uint8_t* sm_pt = sm + kBwdOffPT;
     uint8_t* sm_dst = sm + kBwdOffDST;
-    float* lse2 = reinterpret_cast<float*>(sm + kBwdOffVec);
-    float* delta = lse2 + 256;
-    float* pcol = lse2 + 512;   // p(query i, key x)
-    float* dscol = lse2 + 768;  // ds(query i, key x)
-    float* prow = lse2 + 1024;  // p(query x, key r)
-    float* dsrow = lse2 + 1280; // ds(query x, key r)
+    float* lse2 = reinterpret_cast<float*>(sm + kBwdOffVec);  // lse * log2(e), +inf past the last tensor-core query
+    float* delta = lse2 + 256;   // rowsum(dO * O)
+    float* pcol = lse2 + 512;    // p(query i, key x)
+    float* dscol = lse2 + 768;   // ds(query i, key x)
+    float* prow = lse2 + 1024;   // p(query x, key r)
+    float* dsrow = lse2 + 1280;  // ds(query x, key r)
     float* qx = reinterpret_cast<float*>(sm + kBwdOffX);
     float* kx = qx + 64;
     float* vx = qx + 128;
     float* dox = qx + 192;
-    float* scal = qx + 256;  // [0] p_xx, [1] ds_xx
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kBwdOffBar);  // 0 loads, 1 S^T/dP^T, 2 P^T/dS^T, 3 tile done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    float* scal = qx + 256;  // [0] p_xx, [1] ds_xx, [2] lse2_x, [3] delta_x
+    // mbarriers: 0 first block's operands landed, 1 all operands landed, 2 S^T / dP^T ready, 3 / 4 P^T and dS^T
+    // columns [0, 64) / [64, 128) of the block stored, 5 key tile's MMAs done, 6 edge vectors ready
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kBwdOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, n = blockIdx.y;
     const int D = p.heads * kHd, nv = p.nv, nt = p.n_tiles;
     const size_t vbase = (static_cast<size_t>(n) * p.heads + h) * p.T;
-    const float lse2_x = p.lse[vbase + nv] * kLog2e, delta_x = p.delta[vbase + nv];
     const size_t cta_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
     if (warp == 0) PCG_TRACE(0);
+
+    // delta = rowsum(dO * O) per query needs O, which no MMA reads: the elementwise warps fetch their rows of O and
+    // dO straight from global / L2 (eight lanes share a 128-byte row, four rows per step) at kernel entry, so the
+    // latency hides behind the setup and the operand loads.
+    uint4 xo[8], xd[8];
+    if (warp < 8) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int row = warp * 32 + it * 4 + (lane >> 3);
+            const size_t off = (static_cast<size_t>(n) * p.T + min(row, nv)) * D + h * kHd + (lane & 7) * 8;
+            xo[it] = *reinterpret_cast<const uint4*>(p.out + off);
+            xd[it] = *reinterpret_cast<const uint4*>(p.d_out + off);
+        }
+    }
 
     if (warp == 8) {
         if (lane == 0) {
             mbar_init(&bars[0], 1);
             mbar_init(&bars[1], 1);
-            mbar_init(&bars[2], 8);
-            mbar_init(&bars[3], 1);
+            mbar_init(&bars[2], 1);
+            mbar_init(&bars[3], 8);
+            mbar_init(&bars[4], 8);
+            mbar_init(&bars[5], 1);
+            mbar_init(&bars[6], 3);
             fence_barrier_init();
-            tma_prefetch_desc(&map_qkv);
-            tma_prefetch_desc(&map_do);
+            mbar_arrive_expect_tx(&bars[0], 4 * kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[0], sm_k, D + h * kHd, 0, n, kEvictFirst);
+            tma_load_3d(&map_qkv, &bars[0], sm_q, h * kHd, 0, n, kEvictFirst);
+            tma_load_3d(&map_qkv, &bars[0], sm_v, 2 * D + h * kHd, 0, n, kEvictFirst);
+            tma_load_3d(&map_do, &bars[0], sm_do, h * kHd, 0, n, kEvictFirst);
+            if (nt > 1) {
+                mbar_arrive_expect_tx(&bars[1], 4 * kBlkBytes);
+                tma_load_3d(&map_qkv, &bars[1], sm_q + kBlkBytes, h * kHd, 128, n, kEvictFirst);
+                tma_load_3d(&map_do, &bars[1], sm_do + kBlkBytes, h * kHd, 128, n, kEvictFirst);
+                tma_load_3d(&map_qkv, &bars[1], sm_k + kBlkBytes, D + h * kHd, 128, n, kEvictFirst);
+                tma_load_3d(&map_qkv, &bars[1], sm_v + kBlkBytes, 2 * D + h * kHd, 128, n, kEvictFirst);
+            } else {
+                mbar_arrive(&bars[1]);
+            }
         }
         __syncwarp();
         tmem_alloc(tmem_slot, 512);
@@ -544,10 +666,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     } else if (warp < 8) {
         const int t = threadIdx.x;
         lse2[t] = (t < nv) ? p.lse[vbase + t] * kLog2e : INFINITY;
-        delta[t] = (t < nv) ? p.delta[vbase + t] : 0.f;
     } else {
-        const bf16* xq = p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd;
-        if (warp == 9) load_row_f32(qx, xq, lane), load_row_f32(dox, p.d_out + (static_cast<size_t>(n) * p.T + nv) * D + h * kHd, lane);
+        const size_t rowx = static_cast<size_t>(n) * p.T + nv;
+        const bf16* xq = p.qkv + rowx * 3 * D + h * kHd;
+        if (warp == 9) {
+            load_row_f32(qx, xq, lane);
+            load_row_f32(dox, p.d_out + rowx * D + h * kHd, lane);
+            const uint32_t o2 = *reinterpret_cast<const uint32_t*>(p.out + rowx * D + h * kHd + 2 * lane);
+            const float dx = warp_sum(fmaf(bf_lo(o2), dox[2 * lane], bf_hi(o2) * dox[2 * lane + 1]));
+            if (lane == 0) scal[2] = p.lse[vbase + nv] * kLog2e, scal[3] = dx;
+        }
         if (warp == 10) load_row_f32(kx, xq + D, lane);
         if (warp == 11) load_row_f32(vx, xq + 2 * D, lane);
     }
@@ -558,121 +686,162 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
     if (warp == 8) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars[0], 4 * nt * kBlkBytes);
-            for (int i = 0; i < nt; ++i) {
-                tma_load_3d(&map_qkv, &bars[0], sm_k + i * kBlkBytes, D + h * kHd, i * 128, n, kEvictFirst);
-                tma_load_3d(&map_qkv, &bars[0], sm_q + i * kBlkBytes, h * kHd, i * 128, n, kEvictFirst);
-                tma_load_3d(&map_qkv, &bars[0], sm_v + i * kBlkBytes, 2 * D + h * kHd, i * 128, n, kEvictFirst);
-                tma_load_3d(&map_do, &bars[0], sm_do + i * kBlkBytes, h * kHd, i * 128, n, kEvictFirst);
-            }
-            mbar_wait(&bars[0], 0);
-            PCG_TRACE(1);
-            tc_fence_after();
             const int n_blocks = nt * nt;
             // block b = (key tile j, query block i), j-major; widths of the query blocks
             auto width = [&](int i) { return min(128, ((nv - 128 * i) + 15) & ~15); };
+            mbar_wait(&bars[0], 0);
+            PCG_TRACE(1);
+            tc_fence_after();
             mma_tile_x_rows(tmem + kColST, sm_k, sm_q, width(0));    // S^T  = K_0 Q_0^T
             mma_tile_x_rows(tmem + kColDPT, sm_v, sm_do, width(0));  // dP^T = V_0 dO_0^T
-            umma_commit(&bars[1]);
+            umma_commit(&bars[2]);
+            mbar_wait(&bars[1], 0);
+            tc_fence_after();
             for (int b = 0; b < n_blocks; ++b) {
                 const int j = b / nt, i = b - j * nt;
-                const int ksteps = width(i) >> 4;
-                mbar_wait(&bars[2], b & 1);  // P^T and dS^T of block b are in shared memory, S^T / dP^T consumed
+                const int ksteps = width(i) >> 4, k_lo = min(ksteps, 4);
+                const uint8_t* do_i = sm_do + i * kBlkBytes;
+                const uint8_t* q_i = sm_q + i * kBlkBytes;
+                // columns [0, 64) of P^T / dS^T are stored: first half of dV_j += P^T dO_i and dK_j += dS^T Q_i
+                mbar_wait(&bars[3], b & 1);
+                tc_fence_after();
+                mma_blocks_x_cols(tmem + kColDV, sm_pt, do_i, k_lo, i != 0);
+                mma_blocks_x_cols(tmem + kColDK, sm_dst, q_i, k_lo, i != 0);
+                // all columns stored (and S^T / dP^T consumed)
+                mbar_wait(&bars[4], b & 1);
                 PCG_TRACE(16 + b);
                 tc_fence_after();
-                mma_blocks_x_cols(tmem + kColDV, sm_pt, sm_do + i * kBlkBytes, ksteps, i != 0);   // dV_j += P^T dO_i
-                mma_blocks_x_cols(tmem + kColDK, sm_dst, sm_q + i * kBlkBytes, ksteps, i != 0);   // dK_j += dS^T Q_i
+                if (ksteps > 4) {
+                    mma_blocks_x_cols(tmem + kColDV, sm_pt + kBlkBytes, do_i + 4 * 2048, ksteps - 4, true);
+                    mma_blocks_x_cols(tmem + kColDK, sm_dst + kBlkBytes, q_i + 4 * 2048, ksteps - 4, true);
+                }
                 mma_rows_t_x_cols(tmem + kColDQ + 64 * i, sm_dst, sm_k + j * kBlkBytes, 8, j != 0);  // dQ_i += dS K_j
-                if (i == nt - 1) umma_commit(&bars[3]);  // dV_j, dK_j complete (and dQ after the last tile)
+                if (i == nt - 1) umma_commit(&bars[5]);  // dV_j, dK_j complete (and dQ after the last tile)
                 if (b + 1 < n_blocks) {
                     const int j2 = (b + 1) / nt, i2 = (b + 1) - j2 * nt;
                     mma_tile_x_rows(tmem + kColST, sm_k + j2 * kBlkBytes, sm_q + i2 * kBlkBytes, width(i2));
                     mma_tile_x_rows(tmem + kColDPT, sm_v + j2 * kBlkBytes, sm_do + i2 * kBlkBytes, width(i2));
-                    umma_commit(&bars[1]);
+                    umma_commit(&bars[2]);
                 }
             }
         }
-    } else {
-        mbar_wait(&bars[0], 0);  // Q, K, V, dO are in shared memory
-        if (warp < 8) {
-            // edge products that need one dot product per token: thread t = query t (column x of S) and key t (row x)
-            const int t = threadIdx.x;
+    } else if (warp >= 9) {
+        // edge token x = nv: column x (key x against every query) and row x (query x against every key) of the
+        // score matrix, one dot product per token and side, then the three matrix-vector products for row x of
+        // dV, dK and dQ.  Runs beside the tensor-core pipeline; the epilogues pick the vectors up at the end.
+        named_bar_sync(1, kBwdThreads - 32);  // delta[] is complete
+        mbar_wait(&bars[0], 0);
+        mbar_wait(&bars[1], 0);
+        const float lse2_x = scal[2], delta_x = scal[3];
+        for (int t = (warp - 9) * 32 + lane; t < 256; t += 96) {
+            float pc = 0.f, dsc = 0.f, pr = 0.f, dsr = 0.f;
             if (t < nv) {
-                const float pc = exp2f(fmaf(row_dot(sm_q, t, kx), kLog2e, -lse2[t]));
-                pcol[t] = pc;
-                dscol[t] = pc * (row_dot(sm_do, t, vx) - delta[t]);
-                const float pr = exp2f(fmaf(row_dot(sm_k, t, qx), kLog2e, -lse2_x));
-                prow[t] = pr;
-                dsrow[t] = pr * (row_dot(sm_v, t, dox) - delta_x);
-            } else {
-                pcol[t] = dscol[t] = prow[t] = dsrow[t] = 0.f;
+                pc = exp2f(fmaf(row_dot(sm_q, t, kx), kLog2e, -lse2[t]));
+                dsc = pc * (row_dot(sm_do, t, vx) - delta[t]);
+                pr = exp2f(fmaf(row_dot(sm_k, t, qx), kLog2e, -lse2_x));
+                dsr = pr * (row_dot(sm_v, t, dox) - delta_x);
             }
-            if (t == 0) {
-                float sxx = 0.f, dpxx = 0.f;
-                for (int d = 0; d < 64; ++d) sxx = fmaf(qx[d], kx[d], sxx), dpxx = fmaf(dox[d], vx[d], dpxx);
-                const float pxx = exp2f(fmaf(sxx, kLog2e, -lse2_x));
-                scal[0] = pxx;
-                scal[1] = pxx * (dpxx - delta_x);
-            }
+            pcol[t] = pc, dscol[t] = dsc, prow[t] = pr, dsrow[t] = dsr;
         }
-        named_bar_sync(1, kBwdThreads - 32);  // edge vectors visible to the elementwise and the edge warps
-        if (warp == 0) PCG_TRACE(2);
-        if (warp >= 9) {
-            bf16* gx = p.d_qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd;
-            if (warp == 9) edge_gemv(pcol, sm_do, nv, scal[0], dox, gx + 2 * D, 1.0f, lane);  // dV_x
-            if (warp == 10) edge_gemv(dscol, sm_q, nv, scal[1], qx, gx + D, 1.0f, lane);       // dK_x
-            if (warp == 11) edge_gemv(dsrow, sm_k, nv, scal[1], kx, gx, 1.0f, lane);           // dQ_x
-            if (warp == 11) PCG_TRACE(3);
-        } else {
-            const int quarter = warp & 3, half = warp >> 2;
-            const int r = quarter * 32 + lane;  // key row in the tile == TMEM lane
-            const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-            uint8_t* stage = sm + kBwdOffStage + warp * 2048;
-            bf16* gd = p.d_qkv + static_cast<size_t>(n) * p.T * 3 * D + h * kHd + half * 32;
-            int b = 0;
-            for (int j = 0; j < nt; ++j) {
-                const bool row_ok = (j * 128 + r) < nv;
-                for (int i = 0; i < nt; ++i, ++b) {
-                    const int width = min(128, ((nv - 128 * i) + 15) & ~15);
-                    mbar_wait(&bars[1], b & 1);
-                    tc_fence_after();
-                    if (warp == 0) PCG_TRACE(4 + 2 * b);
-                    uint8_t* pt_blk = sm_pt + half * kBlkBytes;
-                    uint8_t* dst_blk = sm_dst + half * kBlkBytes;
+        if (warp == 9 && lane == 0) {
+            float sxx = 0.f, dpxx = 0.f;
+            for (int d = 0; d < 64; ++d) sxx = fmaf(qx[d], kx[d], sxx), dpxx = fmaf(dox[d], vx[d], dpxx);
+            const float pxx = exp2f(fmaf(sxx, kLog2e, -lse2_x));
+            scal[0] = pxx;
+            scal[1] = pxx * (dpxx - delta_x);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[6]);
+        mbar_wait(&bars[6], 0);
+        if (warp == 9) PCG_TRACE(2);
+        bf16* gx = p.d_qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd;
+        if (warp == 9) edge_gemv(pcol, sm_do, nv, scal[0], dox, gx + 2 * D, 1.0f, lane);  // dV_x
+        if (warp == 10) edge_gemv(dscol, sm_q, nv, scal[1], qx, gx + D, 1.0f, lane);       // dK_x
+        if (warp == 11) edge_gemv(dsrow, sm_k, nv, scal[1], kx, gx, 1.0f, lane);           // dQ_x
+        if (warp == 11) PCG_TRACE(3);
+    } else {
+        const int quarter = warp & 3, phase = warp >> 2;
+        const int r = quarter * 32 + lane;  // key row in the tile == TMEM lane
+        const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint8_t* stage = sm + kBwdOffStage + warp * 2048;
+        bf16* gd = p.d_qkv + static_cast<size_t>(n) * p.T * 3 * D + h * kHd + phase * 32;
+        // delta = rowsum(dO * O): reduce the chunks loaded at kernel entry over the 8 lanes of each row
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = half * 64 + cc * 32;
-                        if (c + 32 <= width)
-                            bwd_chunk<32>(trow + kColST, trow + kColDPT, c, lse2 + i * 128, delta + i * 128, row_ok,
-                                          pt_blk, dst_blk, r);
-                        else if (c < width)
-                            bwd_chunk<16>(trow + kColST, trow + kColDPT, c, lse2 + i * 128, delta + i * 128, row_ok,
-                                          pt_blk, dst_blk, r);
-                    }
-                    fence_proxy_async();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars[2]);
-                    if (warp == 0) PCG_TRACE(5 + 2 * b);
-                }
-                // key tile j finished: dV_j and dK_j (+ the edge query's contribution) -> global
-                mbar_wait(&bars[3], j & 1);
-                tc_fence_after();
-                if (warp == 0) PCG_TRACE(12 + j);
-                const int row0 = j * 128 + quarter * 32;
-                bwd_epilogue(trow + kColDV + half * 32, prow[j * 128 + r], dox + half * 32, stage, lane, gd + 2 * D,
-                             static_cast<size_t>(3) * D, row0, nv);
-                bwd_epilogue(trow + kColDK + half * 32, dsrow[j * 128 + r], qx + half * 32, stage, lane, gd + D,
-                             static_cast<size_t>(3) * D, row0, nv);
-                tc_fence_before();
-            }
-            // dQ_i (+ the edge key's contribution)
-            for (int i = 0; i < nt; ++i)
-                bwd_epilogue(trow + kColDQ + 64 * i + half * 32, dscol[i * 128 + r], kx + half * 32, stage, lane, gd,
-                             static_cast<size_t>(3) * D, i * 128 + quarter * 32, nv);
+        for (int it = 0; it < 8; ++it) {
+            const int row = warp * 32 + it * 4 + (lane >> 3);
+            float d = chunk_dot(xo[it], xd[it]);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            if ((lane & 7) == 0) delta[row] = (row < nv) ? d : 0.f;
         }
+        named_bar_sync(1, kBwdThreads - 32);
+        if (warp == 0) PCG_TRACE(20);
+        int b = 0;
+        for (int j = 0; j < nt; ++j) {
+            const bool row_ok = (j * 128 + r) < nv;
+            for (int i = 0; i < nt; ++i, ++b) {
+                const int width = min(128, ((nv - 128 * i) + 15) & ~15);
+                const float* l2 = lse2 + i * 128;
+                const float* dl = delta + i * 128;
+                mbar_wait(&bars[2], b & 1);
+                tc_fence_after();
+                if (warp == 0) PCG_TRACE(4 + 2 * b);
+                // this warp's columns: [32 phase, +32) of the first 64-column block, then of the second; 16 at a
+                // time with the next TMEM load in flight behind the arithmetic
+                const int c0 = phase * 32, c1 = 64 + phase * 32;
+                uint32_t sa[16], da[16], sb[16], db[16];
+                Cols16 o;
+                if (c0 < width) tmem_ld<16>(trow + kColST + c0, sa), tmem_ld<16>(trow + kColDPT + c0, da);
+                tmem_wait_ld();
+                if (c0 + 16 < width) tmem_ld<16>(trow + kColST + c0 + 16, sb), tmem_ld<16>(trow + kColDPT + c0 + 16, db);
+                if (c0 < width) {
+                    o = bwd_cols16(sa, da, l2 + c0, dl + c0, row_ok);
+                    bwd_store16(o, sm_pt, sm_dst, r, c0 >> 3);
+                }
+                tmem_wait_ld();
+                if (c1 < width) tmem_ld<16>(trow + kColST + c1, sa), tmem_ld<16>(trow + kColDPT + c1, da);
+                if (c0 + 16 < width) {
+                    o = bwd_cols16(sb, db, l2 + c0 + 16, dl + c0 + 16, row_ok);
+                    bwd_store16(o, sm_pt, sm_dst, r, (c0 + 16) >> 3);
+                }
+                tmem_wait_ld();
+                if (c1 + 16 < width) tmem_ld<16>(trow + kColST + c1 + 16, sb), tmem_ld<16>(trow + kColDPT + c1 + 16, db);
+                if (c1 < width) o = bwd_cols16(sa, da, l2 + c1, dl + c1, row_ok);
+                // the first block's stores have drained behind the arithmetic above: this fence is cheap
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[3]);
+                if (c1 < width) bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 - 64) >> 3);
+                tmem_wait_ld();
+                if (c1 + 16 < width) {
+                    o = bwd_cols16(sb, db, l2 + c1 + 16, dl + c1 + 16, row_ok);
+                    bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 + 16 - 64) >> 3);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[4]);
+                if (warp == 0) PCG_TRACE(5 + 2 * b);
+            }
+            // key tile j finished: dV_j and dK_j (+ the edge query's contribution) -> global
+            if (j == 0) mbar_wait(&bars[6], 0);
+            mbar_wait(&bars[5], j & 1);
+            tc_fence_after();
+            if (warp == 0) PCG_TRACE(12 + j);
+            const int row0 = j * 128 + quarter * 32;
+            bwd_epilogue(trow + kColDV + phase * 32, prow[j * 128 + r], dox + phase * 32, stage, lane, gd + 2 * D,
+                         static_cast<size_t>(3) * D, row0, nv);
+            bwd_epilogue(trow + kColDK + phase * 32, dsrow[j * 128 + r], qx + phase * 32, stage, lane, gd + D,
+                         static_cast<size_t>(3) * D, row0, nv);
+            tc_fence_before();
+        }
+        // dQ_i (+ the edge key's contribution)
+        for (int i = 0; i < nt; ++i)
+            bwd_epilogue(trow + kColDQ + 64 * i + phase * 32, dscol[i * 128 + r], kx + phase * 32, stage, lane, gd,
+                         static_cast<size_t>(3) * D, i * 128 + quarter * 32, nv);
+        if (warp == 0) PCG_TRACE(14);
     }
-    if (warp == 0) PCG_TRACE(14);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) PCG_TRACE(15);
@@ -741,6 +910,10 @@ int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols) {
 bool use_tc(int T) { return T >= 66 && T <= 257; }
 
 long long* g_trace = nullptr;
+int g_fwd_stagger = []() {
+    const char* e = getenv("PCG_ATTN_STAGGER");
+    return e != nullptr ? atoi(e) : 5000;
+}();
 
 bool g_force_legacy = []() {
     const char* e = getenv("PCG_ATTN_LEGACY");
@@ -779,8 +952,15 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     }
     const int nv = T - 1;
     FwdParams p{T, heads, nv, (nv + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
-                g_trace};
-    attn_fwd_tc_kernel<<<dim3((nv + 127) / 128, heads, n), kFwdThreads, kFwdSmemBytes, s>>>(map, p);
+                g_trace, 2 * sm_count(), g_fwd_stagger};
+    static const int smem_pad = []() {  // experiment: PCG_ATTN_FWD_ONE=1 forces one CTA per SM
+        const char* e = getenv("PCG_ATTN_FWD_ONE");
+        return (e != nullptr && e[0] == '1') ? 40 * 1024 : 0;
+    }();
+    if (smem_pad)
+        PCG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kFwdSmemBytes + smem_pad));
+    attn_fwd_tc_kernel<<<dim3((nv + 127) / 128, heads, n), kFwdThreads, kFwdSmemBytes + smem_pad, s>>>(map, p);
     PCG_LAUNCH_CHECK("attn_fwd_tc_kernel");
     return 0;
 }
@@ -792,8 +972,10 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
     PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "pcg_attn_bwd: n and heads must be <= 65535");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ProfileScope prof(PCG_PROF_ATTN_BWD, 8.0 * T * T * kHd * heads * n, s);
-    if (int rc = attn_delta(out, d_out, delta_ws, n, T, heads, s)) return rc;
-    if (g_force_legacy || !use_tc(T)) return attn_bwd_legacy(qkv, d_out, lse, delta_ws, d_qkv, n, T, heads, 0, s);
+    if (g_force_legacy || !use_tc(T)) {
+        if (int rc = attn_delta(out, d_out, delta_ws, n, T, heads, s)) return rc;
+        return attn_bwd_legacy(qkv, d_out, lse, delta_ws, d_qkv, n, T, heads, 0, s);
+    }
     const int D = heads * kHd;
     CUtensorMap map, map_do;
     if (int rc = make_map3(&map, qkv, n, T, 3 * D)) return rc;
@@ -804,8 +986,8 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
         configured = true;
     }
     const int nv = T - 1;
-    BwdParams p{T, heads, nv, (nv + 127) / 128, static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_out),
-                lse, delta_ws, static_cast<bf16*>(d_qkv), g_trace};
+    BwdParams p{T,   heads, nv, (nv + 127) / 128, static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
+                static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace};  // delta is computed in-kernel
     attn_bwd_tc_kernel<<<dim3(heads, n), kBwdThreads, kBwdSmemBytes, s>>>(map, map_do, p);
     PCG_LAUNCH_CHECK("attn_bwd_tc_kernel");
     return 0;
