@@ -145,10 +145,13 @@ int pcg_attn_bwd(const void *qkv, const void *out, const void *d_out, const floa
  * enc_out (nullable) f32 [n,E] normalised (or raw if !normalize) encodings.
  * d_enc (nullable) f32 [n,E]: an upstream gradient w.r.t. the encodings; when given it replaces the loss
  *   gradient (this is autograd through encode_images for callers other than the CLIP loss).
- * dx (nullable) f32 [n*T, D]: CLS rows receive d(loss)/dx, all other rows are zeroed. dx_bf16 likewise. */
+ * dx (nullable) f32 [n*T, D]: CLS rows receive d(loss)/dx, all other rows are zeroed. dx_bf16 likewise.
+ * workspace: pcg_head_workspace_bytes(n, D, E) bytes of device scratch (the batched projection's operands). */
+size_t pcg_head_workspace_bytes(int n, int D, int E);
 int pcg_head_loss(const float *x, const float *ln_g, const float *ln_b, const float *proj, const float *targets,
                   const float *tweights, int n, int T, int D, int E, int M, float scale, int normalize,
-                  float *loss_sum, float *enc_out, const float *d_enc, float *dx, void *dx_bf16, void *stream);
+                  float *loss_sum, float *enc_out, const float *d_enc, float *dx, void *dx_bf16, float *workspace,
+                  void *stream);
 
 /* ---- whole path ------------------------------------------------------------------------------------------ */
 /* bytes of scratch (transient) and stash (activations kept for backward) for n cutouts. */

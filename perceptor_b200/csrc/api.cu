@@ -133,6 +133,7 @@ struct Work {
     uint16_t* dqkv;     // [M,3D]
     uint16_t* d_o;      // [M,D]
     float* delta;       // [n*heads*T]
+    float* head_ws;     // pcg_head_workspace_bytes
     void* nostash;      // forward-only stash region
     size_t total;
 };
@@ -150,6 +151,7 @@ Work carve_work(void* base, const pcg_vit_config& c, int n) {
     w.dqkv = b.take<uint16_t>(M * 3 * D);
     w.d_o = b.take<uint16_t>(M * D);
     w.delta = b.take<float>(static_cast<size_t>(n) * c.heads * c.tokens);
+    w.head_ws = b.take<float>(pcg_head_workspace_bytes(n, c.width, c.embed) / sizeof(float));
     w.nostash = base ? static_cast<uint8_t*>(base) + b.off : nullptr;
     b.off += carve_stash(nullptr, c, n, 1).total;
     w.total = b.off;
@@ -269,7 +271,7 @@ extern "C" int pcg_guidance_fwd(const pcg_guidance_args* a, void* stream) {
     }
     PCG_TRY(pcg_head_loss(stash_x(st, c.layers, keep), w.ln_post_g, w.ln_post_b, w.proj, a->targets, a->tweights, n, T, D,
                           c.embed, a->targets ? a->n_targets : 0, a->loss_scale, a->normalize, a->loss_sum, a->enc_out,
-                          nullptr, nullptr, nullptr, stream));
+                          nullptr, nullptr, nullptr, wk.head_ws, stream));
     return 0;
 }
 
@@ -286,7 +288,7 @@ extern "C" int pcg_guidance_bwd(const pcg_guidance_args* a, void* stream) {
     // head: recompute the (tiny) forward of the head and emit d(loss)/dx at the class-token rows
     PCG_TRY(pcg_head_loss(stash_x(st, c.layers, true), w.ln_post_g, w.ln_post_b, w.proj, a->targets, a->tweights, n, T, D,
                           c.embed, a->targets ? a->n_targets : 0, a->d_enc ? 1.0f : a->loss_scale, a->normalize, nullptr,
-                          nullptr, a->d_enc, wk.dx, wk.dxb, stream));
+                          nullptr, a->d_enc, wk.dx, wk.dxb, wk.head_ws, stream));
     for (int l = c.layers - 1; l >= 0; --l) {
         const pcg_layer_weights& lw = w.layers_host[l];
         const LayerStash ls = layer_stash(st, l, true);

@@ -231,24 +231,19 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;
 }
 
+// The head is five small launches batched over cutouts, so that the projection matrix (3 MB for ViT-L/14) is read
+// once per 16-cutout tile instead of twice per cutout:
+//   head_ln_kernel      y  = ln_post(x[CLS])                       one CTA per cutout
+//   head_gemm_kernel    z  = y @ proj                              16 x 64 output tiles
+//   head_dist_kernel    e = z / |z|, loss, dz = d(loss)/dz         one CTA per cutout
+//   head_gemm_kernel    dy = dz @ proj^T
+//   head_ln_bwd_kernel  dx[CLS] = ln_post'(dy)                     one CTA per cutout
 __global__ void __launch_bounds__(kHeadThreads)
-head_loss_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                 const float* __restrict__ proj, const float* __restrict__ targets, const float* __restrict__ tweights,
-                 int T, int D, int E, int M, float scale, int normalize, float* __restrict__ loss_sum,
-                 float* __restrict__ enc_out, const float* __restrict__ d_enc, float* __restrict__ dx,
-                 bf16* __restrict__ dx_bf16) {
-    extern __shared__ float sm[];
-    float* xhat = sm;        // [D]
-    float* ybuf = sm + D;    // [D]   ln_post output, later d(ln_post output)
-    float* ebuf = sm + 2 * D;       // [E] z, then e
-    float* gbuf = sm + 2 * D + E;   // [E] de, then dz
+head_ln_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ ln_b, int T, int D,
+               float* __restrict__ y) {
     __shared__ float red[kHeadThreads / 32];
-
-    const int n = blockIdx.x;
-    const int tid = threadIdx.x;
+    const int n = blockIdx.x, tid = threadIdx.x;
     const float* xr = x + static_cast<size_t>(n) * T * D;  // CLS row
-
-    // ln_post
     float s = 0.f;
     for (int d = tid; d < D; d += kHeadThreads) s += xr[d];
     const float mean = block_sum(s, red) / D;
@@ -258,37 +253,78 @@ head_loss_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, co
         q += c * c;
     }
     const float rstd = 1.0f / sqrtf(block_sum(q, red) / D + kLnEps);
-    for (int d = tid; d < D; d += kHeadThreads) {
-        const float xh = (xr[d] - mean) * rstd;
-        xhat[d] = xh;
-        ybuf[d] = xh * ln_g[d] + ln_b[d];
+    for (int d = tid; d < D; d += kHeadThreads) y[static_cast<size_t>(n) * D + d] = (xr[d] - mean) * rstd * ln_g[d] + ln_b[d];
+}
+
+// C[n, N] = A[n, K] @ B with B = Bm[K, N] (kTransB = false) or B = Bm[N, K]^T (kTransB = true), fp32 on the CUDA
+// cores: 16 x 64 tile per CTA, 32-deep K chunks through shared memory, thread = 1 row x 4 columns.
+constexpr int kHgRows = 16, kHgCols = 64, kHgK = 32;
+template <bool kTransB>
+__global__ void __launch_bounds__(kHeadThreads)
+head_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int n, int N, int K) {
+    __shared__ float As[kHgRows][kHgK + 1];
+    __shared__ float Bs[kHgK][kHgCols + 4];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.y * kHgRows, c0 = blockIdx.x * kHgCols;
+    const int row = tid >> 4, col = (tid & 15) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += kHgK) {
+        for (int i = tid; i < kHgRows * kHgK; i += kHeadThreads) {
+            const int r = i / kHgK, k = i - r * kHgK;
+            As[r][k] = (n0 + r < n && k0 + k < K) ? A[static_cast<size_t>(n0 + r) * K + k0 + k] : 0.f;
+        }
+        for (int i = tid; i < kHgK * kHgCols; i += kHeadThreads) {
+            if (kTransB) {  // Bm rows index the output column, contiguous along k
+                const int c = i / kHgK, k = i - c * kHgK;
+                Bs[k][c] = (c0 + c < N && k0 + k < K) ? __ldg(Bm + static_cast<size_t>(c0 + c) * K + k0 + k) : 0.f;
+            } else {
+                const int k = i / kHgCols, c = i - k * kHgCols;
+                Bs[k][c] = (c0 + c < N && k0 + k < K) ? __ldg(Bm + static_cast<size_t>(k0 + k) * N + c0 + c) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kHgK; ++k) {
+            const float a = As[row][k];
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][col]);
+            acc[0] = fmaf(a, b.x, acc[0]);
+            acc[1] = fmaf(a, b.y, acc[1]);
+            acc[2] = fmaf(a, b.z, acc[2]);
+            acc[3] = fmaf(a, b.w, acc[3]);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // z = y @ proj   (proj [D,E] row-major: threads sweep e, coalesced)
-    for (int e = tid; e < E; e += kHeadThreads) {
-        float acc = 0.f;
-#pragma unroll 4
-        for (int d = 0; d < D; ++d) acc = fmaf(ybuf[d], __ldg(proj + static_cast<size_t>(d) * E + e), acc);
-        ebuf[e] = acc;
+    if (n0 + row < n) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c0 + col + j < N) C[static_cast<size_t>(n0 + row) * N + c0 + col + j] = acc[j];
     }
-    __syncthreads();
+}
+
+// e = z / |z| (or z), spherical-distance loss against every target and dz = d(loss * scale)/dz (or the pull-back of
+// an upstream gradient d_enc through the normalisation)
+__global__ void __launch_bounds__(kHeadThreads)
+head_dist_kernel(const float* __restrict__ z, const float* __restrict__ targets, const float* __restrict__ tweights,
+                 int E, int M, float scale, int normalize, float* __restrict__ loss_sum, float* __restrict__ enc_out,
+                 const float* __restrict__ d_enc, float* __restrict__ dz) {
+    extern __shared__ float sm[];
+    float* ebuf = sm;      // [E]
+    float* gbuf = sm + E;  // [E] d/de
+    __shared__ float red[kHeadThreads / 32];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const float* zr = z + static_cast<size_t>(n) * E;
     float zz = 0.f;
-    for (int e = tid; e < E; e += kHeadThreads) zz += ebuf[e] * ebuf[e];
+    for (int e = tid; e < E; e += kHeadThreads) zz += zr[e] * zr[e];
     const float znorm = sqrtf(block_sum(zz, red));
     const float inv_norm = normalize ? 1.0f / fmaxf(znorm, 1e-12f) : 1.0f;
     for (int e = tid; e < E; e += kHeadThreads) {
-        const float ev = ebuf[e] * inv_norm;
+        const float ev = zr[e] * inv_norm;
         ebuf[e] = ev;
-        gbuf[e] = 0.f;
+        gbuf[e] = (d_enc != nullptr) ? d_enc[static_cast<size_t>(n) * E + e] : 0.f;
         if (enc_out != nullptr) enc_out[static_cast<size_t>(n) * E + e] = ev;
     }
     __syncthreads();
-    if ((targets == nullptr || M <= 0) && d_enc == nullptr) return;
-    if (d_enc != nullptr) {
-        for (int e = tid; e < E; e += kHeadThreads) gbuf[e] = d_enc[static_cast<size_t>(n) * E + e];
-        M = 0;  // upstream gradient replaces the loss gradient
-    }
-
+    if (d_enc != nullptr) M = 0;  // the upstream gradient replaces the loss gradient
     // spherical distance to every target: d = 2 * asin(r/2)^2, r = |e - t|
     float loss_local = 0.f;
     for (int m = 0; m < M; ++m) {
@@ -310,42 +346,48 @@ head_loss_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, co
         for (int e = tid; e < E; e += kHeadThreads) gbuf[e] += coef * (ebuf[e] - tm[e]);
     }
     if (tid == 0 && loss_sum != nullptr && M > 0) atomicAdd(loss_sum, loss_local * scale);
-    if (dx == nullptr) return;
+    if (dz == nullptr) return;
     __syncthreads();
-
     // through F.normalize: dz = (de - e (e . de)) / |z|
+    float dot = 0.f;
     if (normalize) {
-        float dot = 0.f;
         for (int e = tid; e < E; e += kHeadThreads) dot += ebuf[e] * gbuf[e];
         dot = block_sum(dot, red);
-        for (int e = tid; e < E; e += kHeadThreads) gbuf[e] = (gbuf[e] - ebuf[e] * dot) * inv_norm * scale;
-    } else {
-        for (int e = tid; e < E; e += kHeadThreads) gbuf[e] *= scale;
     }
-    __syncthreads();
-    // dy = proj @ dz   (one warp per d: lanes sweep e, coalesced)
-    {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int d = warp; d < D; d += kHeadThreads / 32) {
-            const float* pr = proj + static_cast<size_t>(d) * E;
-            float acc = 0.f;
-            for (int e = lane; e < E; e += 32) acc = fmaf(__ldg(pr + e), gbuf[e], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) ybuf[d] = acc * ln_g[d];  // g = dy * gamma
-        }
+    for (int e = tid; e < E; e += kHeadThreads)
+        dz[static_cast<size_t>(n) * E + e] = normalize ? (gbuf[e] - ebuf[e] * dot) * inv_norm * scale : gbuf[e] * scale;
+}
+
+// dx[CLS row] = ln_post'(dy): statistics recomputed from x (one 4 KB row)
+__global__ void __launch_bounds__(kHeadThreads)
+head_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ dy, int T, int D,
+                   float* __restrict__ dx, bf16* __restrict__ dx_bf16) {
+    __shared__ float red[kHeadThreads / 32];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const float* xr = x + static_cast<size_t>(n) * T * D;
+    const float* gr = dy + static_cast<size_t>(n) * D;
+    float s = 0.f;
+    for (int d = tid; d < D; d += kHeadThreads) s += xr[d];
+    const float mean = block_sum(s, red) / D;
+    float q = 0.f;
+    for (int d = tid; d < D; d += kHeadThreads) {
+        const float c = xr[d] - mean;
+        q += c * c;
     }
-    __syncthreads();
+    const float rstd = 1.0f / sqrtf(block_sum(q, red) / D + kLnEps);
     float s1 = 0.f, s2 = 0.f;
     for (int d = tid; d < D; d += kHeadThreads) {
-        s1 += ybuf[d];
-        s2 += ybuf[d] * xhat[d];
+        const float g = gr[d] * ln_g[d];
+        s1 += g;
+        s2 += g * (xr[d] - mean) * rstd;
     }
     const float c1 = block_sum(s1, red) / D;
     const float c2 = block_sum(s2, red) / D;
     float* dxr = dx + static_cast<size_t>(n) * T * D;
     bf16* dbr = dx_bf16 ? dx_bf16 + static_cast<size_t>(n) * T * D : nullptr;
     for (int d = tid; d < D; d += kHeadThreads) {
-        const float gval = rstd * (ybuf[d] - c1 - xhat[d] * c2);
+        const float xh = (xr[d] - mean) * rstd;
+        const float gval = rstd * (gr[d] * ln_g[d] - c1 - xh * c2);
         dxr[d] = gval;
         if (dbr) dbr[d] = __float2bfloat16(gval);
     }
@@ -405,23 +447,44 @@ extern "C" int pcg_embed_bwd(const float* dx0, const float* v, const float* gamm
     return 0;
 }
 
+extern "C" size_t pcg_head_workspace_bytes(int n, int D, int E) {
+    if (n <= 0 || D <= 0 || E <= 0) return 0;
+    return (2 * static_cast<size_t>(n) * D + 2 * static_cast<size_t>(n) * E) * sizeof(float);
+}
+
 extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_b, const float* proj,
                              const float* targets, const float* tweights, int n, int T, int D, int E, int M, float scale,
                              int normalize, float* loss_sum, float* enc_out, const float* d_enc, float* dx,
-                             void* dx_bf16, void* stream) {
-    PCG_CHECK_ARG(x && ln_g && ln_b && proj && n > 0 && T > 0 && D > 0 && E > 0, "pcg_head_loss: bad arguments");
+                             void* dx_bf16, float* workspace, void* stream) {
+    PCG_CHECK_ARG(x && ln_g && ln_b && proj && workspace && n > 0 && T > 0 && D > 0 && E > 0,
+                  "pcg_head_loss: bad arguments");
     PCG_CHECK_ARG(M == 0 || (targets && tweights), "pcg_head_loss: targets/tweights missing for M=%d", M);
     PCG_CHECK_ARG(dx == nullptr || M > 0 || d_enc, "pcg_head_loss: a gradient needs targets or d_enc");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t smem = static_cast<size_t>(2 * D + 2 * E) * sizeof(float);
-    PCG_CHECK_ARG(smem <= 48 * 1024, "pcg_head_loss: D=%d E=%d exceed the shared-memory budget", D, E);
-    ProfileScope prof(PCG_PROF_HEAD, (dx ? 6.0 : 0.0) * n * T * D + 8.0 * n * D * E, s);
+    const size_t smem = static_cast<size_t>(2 * E) * sizeof(float);
+    PCG_CHECK_ARG(smem <= 48 * 1024, "pcg_head_loss: E=%d exceeds the shared-memory budget", E);
+    ProfileScope prof(PCG_PROF_HEAD, (dx ? 6.0 : 0.0) * n * T * D + (dx ? 4.0 : 2.0) * n * D * E, s);
+    float* y = workspace;                             // [n, D] ln_post output
+    float* dy = y + static_cast<size_t>(n) * D;       // [n, D]
+    float* z = dy + static_cast<size_t>(n) * D;       // [n, E]
+    float* dz = z + static_cast<size_t>(n) * E;       // [n, E]
     if (dx != nullptr) {
         PCG_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(n) * T * D * sizeof(float), s));
         if (dx_bf16 != nullptr) PCG_CUDA(cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(n) * T * D * 2, s));
     }
-    head_loss_kernel<<<n, kHeadThreads, smem, s>>>(x, ln_g, ln_b, proj, M > 0 ? targets : nullptr, tweights, T, D, E, M,
-                                                   scale, normalize, loss_sum, enc_out, d_enc, dx, static_cast<bf16*>(dx_bf16));
-    PCG_LAUNCH_CHECK("head_loss_kernel");
+    head_ln_kernel<<<n, kHeadThreads, 0, s>>>(x, ln_g, ln_b, T, D, y);
+    PCG_LAUNCH_CHECK("head_ln_kernel");
+    head_gemm_kernel<false><<<dim3(ceil_div(E, kHgCols), ceil_div(n, kHgRows)), kHeadThreads, 0, s>>>(y, proj, z, n, E, D);
+    PCG_LAUNCH_CHECK("head_gemm_kernel");
+    const bool has_loss = targets != nullptr && M > 0;
+    if (!has_loss && d_enc == nullptr && enc_out == nullptr) return 0;
+    head_dist_kernel<<<n, kHeadThreads, smem, s>>>(z, has_loss ? targets : nullptr, tweights, E, has_loss ? M : 0, scale,
+                                                   normalize, loss_sum, enc_out, d_enc, dx ? dz : nullptr);
+    PCG_LAUNCH_CHECK("head_dist_kernel");
+    if (dx == nullptr) return 0;
+    head_gemm_kernel<true><<<dim3(ceil_div(D, kHgCols), ceil_div(n, kHgRows)), kHeadThreads, 0, s>>>(dz, proj, dy, n, D, E);
+    PCG_LAUNCH_CHECK("head_gemm_kernel");
+    head_ln_bwd_kernel<<<n, kHeadThreads, 0, s>>>(x, ln_g, dy, T, D, dx, static_cast<bf16*>(dx_bf16));
+    PCG_LAUNCH_CHECK("head_ln_bwd_kernel");
     return 0;
 }

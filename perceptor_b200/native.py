@@ -88,7 +88,8 @@ SIGNATURES = {
     "pcg_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "pcg_head_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcg_head_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcg_head_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "pcg_workspace_bytes": (C.c_size_t, [C.POINTER(VitConfig), _i]),
     "pcg_stash_bytes": (C.c_size_t, [C.POINTER(VitConfig), _i]),
     "pcg_guidance_fwd": (_i, [C.POINTER(GuidanceArgs), _vp]),

@@ -90,9 +90,10 @@ def head_loss(x, ln_g, ln_b, proj, targets, tweights, n, tokens, scale=1.0, norm
     dx = torch.empty((n * tokens, d), dtype=torch.float32, device=dev) if want_grad else None
     dxb = torch.empty((n * tokens, d), dtype=bf16, device=dev) if want_grad else None
     m = 0 if targets is None else targets.shape[0]
+    ws = torch.empty(native.lib().pcg_head_workspace_bytes(n, d, e) // 4, dtype=torch.float32, device=dev)
     native.check(native.lib().pcg_head_loss(_p(x), _p(ln_g), _p(ln_b), _p(proj), _p(targets), _p(tweights), n, tokens, d,
                                             e, m, float(scale), int(normalize), _p(loss), _p(enc), _p(d_enc), _p(dx),
-                                            _p(dxb), native.stream_ptr()), "pcg_head_loss")
+                                            _p(dxb), _p(ws), native.stream_ptr()), "pcg_head_loss")
     return loss, enc, dx, dxb
 
 
