@@ -7,6 +7,10 @@
 //     fp32 accumulator in tensor memory; eight epilogue warps drain it with tcgen05.ld, transpose each 32 x 32
 //     chunk through a swizzled shared-memory tile and apply the fused epilogue (bias / QuickGELU / residual add /
 //     activation derivative) with fully coalesced global loads and stores; epilogue inputs are prefetched ahead.
+//   * CTAS = 2: a cluster of two CTAs (one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA
+//     stages its own 128 rows of A and HALF of the B tile, so shared memory sees 2/3 of the single-CTA traffic
+//     per flop (the single-CTA 128 x 256 tile is shared-memory-bandwidth bound at ~75 % of the MMA rate, see
+//     tools/ubench.cu); the even CTA issues the MMAs, each CTA drains its own 128 accumulator rows.
 //   * grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x + i*gridDim.x (n fastest so that the CTAs
 //     running concurrently share A row-panels in L2; B (weights) is L2 resident).
 //
@@ -14,6 +18,8 @@
 // 31-39, 43-49, 85-91), which today are eager cuBLAS calls plus separate bias/activation/residual kernels.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -27,16 +33,17 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kCtrlWarps = 4;  // warp 0: TMA producer, warp 1: MMA issuer, warp 2: TMEM allocator, warp 3: spare
-constexpr int kEpiWarps = 8;   // two warpgroups; warp%4 selects the TMEM lane quarter, warpgroup the column half
-constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);
+constexpr int kEpiWarps = 8;   // warps 0-7: two warpgroups; warp % 4 selects the TMEM lane quarter, warp / 4 the column half
+constexpr int kCtrlWarps = 3;  // warp 8: TMA producer, warp 9: MMA issuer, warp 10: TMEM allocator
+constexpr int kWarpTma = kEpiWarps, kWarpMma = kEpiWarps + 1, kWarpAlloc = kEpiWarps + 2;
+constexpr int kThreads = 32 * (kCtrlWarps + kEpiWarps);  // 352: leaves 184 registers per thread for the epilogue
 constexpr int kABytes = BM * BK * 2;
 constexpr int kEpiStageBytes = 32 * 32 * 4;  // per epilogue warp: one 32 x 32 fp32 chunk, XOR-swizzled 16-byte columns
 
-template <int BN>
+template <int BN, int CTAS = 1>
 struct TileCfg {
-    static constexpr int kBBytes = BN * BK * 2;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int kBBytes = BN / CTAS * BK * 2;  // per CTA: a pair splits the B tile by rows
+    static constexpr int kStages = (CTAS == 2) ? 6 : (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     static constexpr int kBarBytes = 256;
     static constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;
@@ -76,11 +83,12 @@ __device__ __forceinline__ float act_and_grad(float h, float& grad) {
     }
 }
 
-template <int BN, int MODE, int ACT>
+template <int BN, int MODE, int ACT, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p) {
-    using Cfg = TileCfg<BN>;
+    using Cfg = TileCfg<BN, CTAS>;
+    constexpr int kTileM = BM * CTAS;  // rows of one output tile (per cluster)
     constexpr int kStages = Cfg::kStages;
     constexpr int kBBytes = Cfg::kBBytes;
 
@@ -101,48 +109,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m = (p.M + BM - 1) / BM;
+    const int num_m = (p.M + kTileM - 1) / kTileM;
     const int num_n = (p.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + BK - 1) / BK;
+    // a CTA pair walks the same tiles; rank 1 owns rows [128, 256) of the tile and B rows [BN/2, BN)
+    const int cta_rank = (CTAS == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int tile0 = static_cast<int>(blockIdx.x) / CTAS;
+    const int tile_step = static_cast<int>(gridDim.x) / CTAS;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kWarpTma && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kWarpMma && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kEpiWarps);
+            mbar_init(&tempty_bar[i], kEpiWarps * CTAS);  // the even CTA's copy collects both CTAs' epilogue warps
         }
         fence_barrier_init();
     }
-    if (warp == 2) {
-        tmem_alloc(tmem_slot, Cfg::kTmemCols);
-        tmem_relinquish();
+    if (warp == kWarpAlloc) {
+        if constexpr (CTAS == 2) {
+            tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();  // barriers visible to the peer before use
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == kWarpTma) {
         // ===================== TMA producer (one thread) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * BM;
-                const int n0 = (tile % num_n) * BN;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                const int m0 = (tile / num_n) * kTileM + cta_rank * BM;
+                const int n0 = (tile % num_n) * BN + cta_rank * (BN / CTAS);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
-                    tma_load_2d(&map_a, &full_bar[stage], smem_a + stage * kABytes, kb * BK, m0, kEvictNormal);
-                    tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * kBBytes, kb * BK, n0, kEvictLast);
+                    if constexpr (CTAS == 2) {
+                        // both CTAs' bytes land on the even CTA's barrier, which alone expects them
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));
+                        tma_load_2d_2sm(&map_a, &full_bar[stage], smem_a + stage * kABytes, kb * BK, m0, kEvictNormal);
+                        tma_load_2d_2sm(&map_b, &full_bar[stage], smem_b + stage * kBBytes, kb * BK, n0, kEvictLast);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
+                        tma_load_2d(&map_a, &full_bar[stage], smem_a + stage * kABytes, kb * BK, m0, kEvictNormal);
+                        tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * kBBytes, kb * BK, n0, kEvictLast);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -150,14 +174,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
@@ -171,10 +195,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 bytes per K=16 step inside the 128-byte swizzle atom (encoded >>4 => +2)
-                        umma_f16(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (CTAS == 2)
+                            umma_f16_2sm(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
+                        else
+                            umma_f16(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                    if constexpr (CTAS == 2) {
+                        umma_commit_2sm(&empty_bar[stage]);  // frees the slot in both CTAs when these MMAs retire
+                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[as]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -182,54 +214,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
             }
         }
-    } else if (warp >= kCtrlWarps) {
+    } else if (warp < kEpiWarps) {
         // TMEM -> registers (thread = row) -> XOR-swizzled per-warp staging tile in smem -> registers
         // (8 lanes = one row's 32 columns) so that every global access is a full, coalesced row segment.
         // Epilogue inputs (residual / pre-activation) are prefetched kDist 32-column chunks ahead, across tile
         // boundaries, to keep >= 64 KB of reads in flight per SM (the epilogue is latency-, not throughput-bound).
         const int quarter = warp & 3;               // TMEM lanes [32*quarter, +32) are the ones this warp may read
-        const int half = (warp - kCtrlWarps) >> 2;  // column half of the tile
+        const int half = warp >> 2;                 // column half of the tile
         constexpr int kHalfN = BN / 2;
         constexpr int kChunks = kHalfN / 32;
         constexpr bool kHasAux = (MODE == PCG_GEMM_RESID_F32 || MODE == PCG_GEMM_DACT);
         constexpr int kAuxWords = (MODE == PCG_GEMM_RESID_F32) ? 4 : 2;  // 32-bit words per lane per row group
-        constexpr int kDistWanted = (MODE == PCG_GEMM_RESID_F32) ? 2 : 4;
+        constexpr int kDistWanted = 2;  // deeper prefetch spills: 2 slots x 8 rows x 16 B (or 8 B) per lane fit the register file
         // the slot of chunk c must be a compile-time constant: kDist has to divide kChunks
         constexpr int kDist = !kHasAux ? 1 : (kChunks % kDistWanted == 0 ? kDistWanted : (kChunks % 2 == 0 ? 2 : kChunks));
-        uint8_t* stage_buf = smem_epi + (warp - kCtrlWarps) * kEpiStageBytes;
+        uint8_t* stage_buf = smem_epi + warp * kEpiStageBytes;
         const int sub_row = lane >> 3;  // row within a 4-row group when reading back
         const int sub_col = lane & 7;   // 16-byte column chunk (4 floats) within the 32-column chunk
         uint32_t auxr[kDist][8][kAuxWords];
         // issue the loads of chunk `c` of tile `t` into slot `c % kDist`
+        // Loads are unconditional (indices clamped into the matrix, the consumer is guarded): a predicated load would
+        // land in a temporary and the copy into the slot would wait for it right here, defeating the prefetch.
         auto prefetch_aux = [&](int t, int c, uint32_t(&dst)[8][kAuxWords]) {
             if constexpr (kHasAux) {
-                if (t < num_tiles) {
-                    const int rb = (t / num_n) * BM + quarter * 32 + sub_row;
-                    const int col = (t % num_n) * BN + half * kHalfN + c * 32 + sub_col * 4;
+                const int tt = min(t, num_tiles - 1);
+                const int rb = (tt / num_n) * kTileM + cta_rank * BM + quarter * 32 + sub_row;
+                const int col = min((tt % num_n) * BN + half * kHalfN + c * 32 + sub_col * 4, p.N - 4);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int grow = rb + i * 4;
-                        if (grow < p.M && col < p.N) {
-                            const size_t off = static_cast<size_t>(grow) * p.ldo + col;
-                            if constexpr (MODE == PCG_GEMM_RESID_F32) {
-                                const uint4 t4 = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.aux) + off);
-                                dst[i][0] = t4.x; dst[i][1] = t4.y; dst[i][kAuxWords - 2] = t4.z; dst[i][kAuxWords - 1] = t4.w;
-                            } else {
-                                const uint2 t2 = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.aux) + off);
-                                dst[i][0] = t2.x; dst[i][1] = t2.y;
-                            }
-                        }
+                for (int i = 0; i < 8; ++i) {
+                    const size_t off = static_cast<size_t>(min(rb + i * 4, p.M - 1)) * p.ldo + col;
+                    if constexpr (MODE == PCG_GEMM_RESID_F32) {
+                        const uint4 t4 = *reinterpret_cast<const uint4*>(static_cast<const float*>(p.aux) + off);
+                        dst[i][0] = t4.x; dst[i][1] = t4.y; dst[i][kAuxWords - 2] = t4.z; dst[i][kAuxWords - 1] = t4.w;
+                    } else {
+                        const uint2 t2 = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.aux) + off);
+                        dst[i][0] = t2.x; dst[i][1] = t2.y;
                     }
                 }
             }
         };
 #pragma unroll
-        for (int d = 0; d < kDist; ++d) prefetch_aux(static_cast<int>(blockIdx.x) + (d / kChunks) * gridDim.x, d % kChunks, auxr[d % kDist]);
+        for (int d = 0; d < kDist; ++d) prefetch_aux(tile0 + (d / kChunks) * tile_step, d % kChunks, auxr[d % kDist]);
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * BM;
+            const int m0 = (tile / num_n) * kTileM + cta_rank * BM;
             const int n0 = (tile % num_n) * BN;
             const int row_base = m0 + quarter * 32;
             const int col_base = n0 + half * kHalfN + sub_col * 4;  // this lane's first column of chunk 0
@@ -287,18 +317,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                 }
                 // slot c % kDist is free again: prefetch the chunk kDist items ahead (possibly of a later tile)
-                prefetch_aux(tile + ((c + kDist) / kChunks) * static_cast<int>(gridDim.x), (c + kDist) % kChunks, auxr[c % kDist]);
+                prefetch_aux(tile + ((c + kDist) / kChunks) * tile_step, (c + kDist) % kChunks, auxr[c % kDist]);
                 __syncwarp();  // staging tile is rewritten by the next chunk
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if constexpr (CTAS == 2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CTAS == 2) {
+        cluster_sync_all();  // neither CTA may exit while the other can still signal its barriers
+        if (warp == kWarpAlloc) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    } else {
+        __syncthreads();
+        if (warp == kWarpAlloc) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -366,37 +403,54 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
     return 0;
 }
 
-template <int BN, int MODE, int ACT>
+template <int BN, int MODE, int ACT, int CTAS>
 int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = TileCfg<BN>;
+    using Cfg = TileCfg<BN, CTAS>;
     static bool configured = false;
     if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::kSmem));
+        PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
         configured = true;
     }
-    const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_tcgen05_kernel<BN, MODE, ACT><<<grid, kThreads, Cfg::kSmem, stream>>>(ma, mb, p);
+    const int tiles = ceil_div(p.M, BM * CTAS) * ceil_div(p.N, BN);
+    const int slots = sm_count() / CTAS;  // clusters (or CTAs) that run concurrently
+    const int grid = (tiles < slots ? tiles : slots) * CTAS;
+    if constexpr (CTAS == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PCG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>, ma, mb, p));
+    } else {
+        gemm_tcgen05_kernel<BN, MODE, ACT, CTAS><<<grid, kThreads, Cfg::kSmem, stream>>>(ma, mb, p);
+    }
     PCG_LAUNCH_CHECK("gemm_tcgen05_kernel");
     return 0;
 }
-template <int BN, int MODE>
+template <int BN, int MODE, int CTAS>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
     if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
-        if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU>(ma, mb, p, stream);
+        if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU, CTAS>(ma, mb, p, stream);
     }
-    return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU>(ma, mb, p, stream);
+    return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU, CTAS>(ma, mb, p, stream);
 }
 
-template <int BN>
+template <int BN, int CTAS = 1>
 int dispatch_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
     switch (mode) {
-        case PCG_GEMM_BF16: return launch_gemm<BN, PCG_GEMM_BF16>(ma, mb, p, s);
-        case PCG_GEMM_BIAS_ACT: return launch_gemm<BN, PCG_GEMM_BIAS_ACT>(ma, mb, p, s);
-        case PCG_GEMM_RESID_F32: return launch_gemm<BN, PCG_GEMM_RESID_F32>(ma, mb, p, s);
-        case PCG_GEMM_DACT: return launch_gemm<BN, PCG_GEMM_DACT>(ma, mb, p, s);
-        case PCG_GEMM_F32: return launch_gemm<BN, PCG_GEMM_F32>(ma, mb, p, s);
+        case PCG_GEMM_BF16: return launch_gemm<BN, PCG_GEMM_BF16, CTAS>(ma, mb, p, s);
+        case PCG_GEMM_BIAS_ACT: return launch_gemm<BN, PCG_GEMM_BIAS_ACT, CTAS>(ma, mb, p, s);
+        case PCG_GEMM_RESID_F32: return launch_gemm<BN, PCG_GEMM_RESID_F32, CTAS>(ma, mb, p, s);
+        case PCG_GEMM_DACT: return launch_gemm<BN, PCG_GEMM_DACT, CTAS>(ma, mb, p, s);
+        case PCG_GEMM_F32: return launch_gemm<BN, PCG_GEMM_F32, CTAS>(ma, mb, p, s);
         default: return set_error(-1, "pcg_gemm_bf16: unknown mode %d", mode);
     }
 }
@@ -423,6 +477,11 @@ int choose_bn(int M, int N) {
     return best;
 }
 
+bool g_pair_enabled = []() {
+    const char* e = getenv("PCG_GEMM_PAIR");
+    return !(e != nullptr && e[0] == '0');
+}();
+
 }  // namespace
 
 int gemm_bf16_impl(int mode, int act, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
@@ -436,14 +495,19 @@ int gemm_bf16_impl(int mode, int act, int M, int N, int K, const void* A, int ld
                    reinterpret_cast<uintptr_t>(out)) % 16 == 0, "pcg_gemm_bf16: operands must be 16-byte aligned");
     PCG_CHECK_ARG(mode != PCG_GEMM_BIAS_ACT || out2, "pcg_gemm_bf16: BIAS_ACT needs out2");
     PCG_CHECK_ARG((mode != PCG_GEMM_RESID_F32 && mode != PCG_GEMM_DACT) || aux, "pcg_gemm_bf16: mode needs aux");
-    const int bn = force_bn ? force_bn : choose_bn(M, N);
+    // CTA pairs (256 x 256 tiles) when the problem fills the 74 pairs with full-width tiles; force_bn 512 forces
+    // them, any other force_bn the single-CTA kernel
+    const bool pair = force_bn ? force_bn == 512
+                               : (g_pair_enabled && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= sm_count() / 2);
+    const int bn = pair ? 256 : (force_bn ? force_bn : choose_bn(M, N));
     CUtensorMap ma, mb;
     int rc = get_tensor_map(&ma, A, M, K, lda, BM);
     if (rc) return rc;
-    rc = get_tensor_map(&mb, B, N, K, ldb, bn);
+    rc = get_tensor_map(&mb, B, N, K, ldb, pair ? 128 : bn);
     if (rc) return rc;
     GemmParams p{M, N, K, bias, aux, out, out2, ldo, act};
     ProfileScope prof(PCG_PROF_GEMM, 2.0 * M * N * K, stream);
+    if (pair) return dispatch_mode<256, 2>(mode, ma, mb, p, stream);
     switch (bn) {
         case 256: return dispatch_mode<256>(mode, ma, mb, p, stream);
         case 192: return dispatch_mode<192>(mode, ma, mb, p, stream);
@@ -460,7 +524,10 @@ extern "C" int pcg_gemm_bf16(int mode, int act, int M, int N, int K, const void*
     return pcg::gemm_bf16_impl(mode, act, M, N, K, A, lda, B, ldb, bias, aux, out, out2, ldo, 0,
                                static_cast<cudaStream_t>(stream));
 }
-extern "C" int pcg_gemm_set_variant(int) { return 0; }  // kept for tools; there is a single epilogue variant now
+extern "C" int pcg_gemm_set_variant(int v) {  // tools / tests: 0 = single-CTA kernels only, 1 = CTA pairs allowed
+    pcg::g_pair_enabled = v != 0;
+    return 0;
+}
 // test hook: force the N tile width (64/128/192/256)
 extern "C" int pcg_gemm_bf16_bn(int bn, int mode, int act, int M, int N, int K, const void* A, int lda, const void* B,
                                 int ldb, const float* bias, const void* aux, void* out, void* out2, int ldo,

@@ -47,7 +47,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
-@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256, 512])  # 512 = CTA pair (cta_group::2, 256 x 256 tiles)
 def test_gemm_plain(cuda_device, m, n, k, bn):
     g = torch.Generator(device="cpu").manual_seed(m * 7 + n * 3 + k)
     a = torch.randn(m, k, generator=g).to(cuda_device, bf16)
@@ -62,7 +62,8 @@ def test_gemm_plain(cuda_device, m, n, k, bn):
 
 @pytest.mark.parametrize("m,n,k", [(300, 3072, 768), (257, 1024, 1024), (4112, 4096, 1024)])
 @pytest.mark.parametrize("act", [native.ACT_QUICKGELU, native.ACT_GELU])
-def test_gemm_epilogues(cuda_device, m, n, k, act):
+@pytest.mark.parametrize("bn", [256, 512])
+def test_gemm_epilogues(cuda_device, m, n, k, act, bn):
     g = torch.Generator(device="cpu").manual_seed(11 + m)
     a = torch.randn(m, k, generator=g).to(cuda_device, bf16)
     b = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(cuda_device, bf16)
@@ -72,16 +73,16 @@ def test_gemm_epilogues(cuda_device, m, n, k, act):
     # bias + activation: the kernel stores act'(h) (for the backward multiply) and act(h)
     hx = (acc + bias).clone().requires_grad_()
     want_grad = torch.autograd.grad(f(hx).sum(), hx)[0]
-    dact_out, act_out = ops.gemm(native.GEMM_BIAS_ACT, a, b, bias=bias, act=act)
+    dact_out, act_out = ops.gemm(native.GEMM_BIAS_ACT, a, b, bias=bias, act=act, bn=bn)
     check_close(dact_out, want_grad, 6e-3, "bias_act: stored derivative")
     check_close(act_out, f(acc + bias), 6e-3, "bias_act: activation")
     # residual
     res = torch.randn(m, n, generator=g).to(cuda_device)
-    out = ops.gemm(native.GEMM_RESID_F32, a, b, bias=bias, aux=res)
+    out = ops.gemm(native.GEMM_RESID_F32, a, b, bias=bias, aux=res, bn=bn)
     check_close(out, res + acc + bias, 2e-5, "residual f32")
     # multiply by the stored activation derivative
     dact = torch.randn(m, n, generator=g).to(cuda_device, bf16)
-    out = ops.gemm(native.GEMM_DACT, a, b, aux=dact, act=act)
+    out = ops.gemm(native.GEMM_DACT, a, b, aux=dact, act=act, bn=bn)
     check_close(out, acc * dact.float(), 4e-3, "dact")
 
 
