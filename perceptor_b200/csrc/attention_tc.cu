@@ -340,6 +340,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
 
     if (warp == 4) {
         if (lane == 0) {
+            const int nblk = (nk + 127) >> 7;
+            // pull the operands of the CTA that takes this slot next (stagger_ctas = CTAs resident at once) into L2;
+            // the tiles of one head share K and V, so only the first tile's CTA prefetches those
+            const size_t next = cta_id + p.stagger_ctas;
+            if (next < static_cast<size_t>(gridDim.x) * gridDim.y * gridDim.z) {
+                const int t2 = static_cast<int>(next % gridDim.x);
+                const int h2 = static_cast<int>((next / gridDim.x) % gridDim.y), n2 = static_cast<int>(next / (gridDim.x * gridDim.y));
+                tma_prefetch_3d(&map_qkv, h2 * kHd, t2 * 128, n2);
+                if (t2 == 0)
+                    for (int i = 0; i < nblk; ++i) {
+                        tma_prefetch_3d(&map_qkv, D + h2 * kHd, i * 128, n2);
+                        tma_prefetch_3d(&map_qkv, 2 * D + h2 * kHd, i * 128, n2);
+                    }
+            }
             mbar_wait(&bars[0], 0);
             PCG_TRACE(2);
             tc_fence_after();
@@ -500,6 +514,7 @@ struct BwdParams {
     const float* lse;
     bf16* d_qkv;
     long long* trace;
+    int wave;  // CTAs resident at once (one per SM): the L2 prefetch distance
 };
 
 // 16 columns of one block for this thread's key row: P^T = exp2(S^T log2e - lse2), dS^T = P^T (dP^T - delta) as
@@ -633,6 +648,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             xo[it] = *reinterpret_cast<const uint4*>(p.out + off);
             xd[it] = *reinterpret_cast<const uint4*>(p.d_out + off);
         }
+        const size_t next = cta_id + p.wave;  // the next head's O rows (its dO rows come with the TMA prefetch)
+        if (next < static_cast<size_t>(gridDim.x) * gridDim.y && threadIdx.x <= nv)
+            prefetch_l2(p.out + (static_cast<size_t>(next / gridDim.x) * p.T + threadIdx.x) * D + (next % gridDim.x) * kHd);
     }
 
     if (warp == 8) {
@@ -689,6 +707,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             const int n_blocks = nt * nt;
             // block b = (key tile j, query block i), j-major; widths of the query blocks
             auto width = [&](int i) { return min(128, ((nv - 128 * i) + 15) & ~15); };
+            // pull the operands of the head that runs on this SM next (one wave ahead) into L2
+            const size_t next = cta_id + p.wave;
+            if (next < static_cast<size_t>(gridDim.x) * gridDim.y) {
+                const int h2 = static_cast<int>(next % gridDim.x), n2 = static_cast<int>(next / gridDim.x);
+                for (int i = 0; i < nt; ++i) {
+                    tma_prefetch_3d(&map_qkv, D + h2 * kHd, i * 128, n2);
+                    tma_prefetch_3d(&map_qkv, h2 * kHd, i * 128, n2);
+                    tma_prefetch_3d(&map_qkv, 2 * D + h2 * kHd, i * 128, n2);
+                    tma_prefetch_3d(&map_do, h2 * kHd, i * 128, n2);
+                }
+            }
             mbar_wait(&bars[0], 0);
             PCG_TRACE(1);
             tc_fence_after();
@@ -987,7 +1016,7 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
     }
     const int nv = T - 1;
     BwdParams p{T,   heads, nv, (nv + 127) / 128, static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
-                static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace};  // delta is computed in-kernel
+                static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace, sm_count()};  // delta: in-kernel
     attn_bwd_tc_kernel<<<dim3(heads, n), kBwdThreads, kBwdSmemBytes, s>>>(map, map_do, p);
     PCG_LAUNCH_CHECK("attn_bwd_tc_kernel");
     return 0;

@@ -213,6 +213,15 @@ __device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, voi
         : "memory");
 }
 
+// TMA prefetch of one box into L2 (no shared memory, no barrier): used to pull the operands of the CTA that will
+// run on this SM next, so its loads hit L2 instead of queueing on HBM with every other SM's.
+__device__ __forceinline__ void tma_prefetch_3d(const void* desc, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major (cute::UMMA::InstrDescriptor
 // bit layout: c_format[4,6) a_format[7,10) b_format[10,13) a_major[15] b_major[16] n>>3 [17,23) m>>4 [24,29)).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
