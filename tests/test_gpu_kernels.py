@@ -250,12 +250,23 @@ def sampler_reference(images, rows5, r):
 
 
 @pytest.mark.parametrize("r,patch", [(224, 32), (224, 14), (336, 14)])
-def test_sampler_forward_backward(cuda_device, r, patch):
+@pytest.mark.parametrize("width,scalar", [(520, 0), (520, 1), (522, 0)])  # 522: rows not 16-byte aligned -> scalar kernels
+def test_sampler_forward_backward(cuda_device, r, patch, width, scalar):
     g = torch.Generator(device="cpu").manual_seed(r + patch)
-    images = torch.rand(2, 3, 400, 520, generator=g)
+    images = torch.rand(2, 3, 400, width, generator=g)
+    # every crop-origin alignment (x0 & 3), crops touching the right / bottom edge, up- and down-scaling, non-square
     rows = [(0, 0, 0, 400, 520), (1, 10, 20, 300, 300), (0, 100, 200, 225, 225), (1, 50, 60, 100, 100),
-            (0, 7, 9, r, r), (1, 0, 100, 390, 150), (0, 176, 296, 224, 224), (1, 3, 5, 33, 47)]
+            (0, 7, 9, r, r), (1, 0, 100, 390, 150), (0, 176, 296, 224, 224), (1, 3, 5, 33, 47),
+            (0, 33, 2, 130, 130), (1, 1, 3, 64, 64), (0, 299, width - 101, 101, 101), (1, 0, 6, 400, 400)]
     rows = np.array(rows, dtype=np.int32)
+    native.lib().pcg_sampler_set_scalar(scalar)
+    try:
+        _check_sampler(cuda_device, r, patch, images, rows, g)
+    finally:
+        native.lib().pcg_sampler_set_scalar(0)
+
+
+def _check_sampler(cuda_device, r, patch, images, rows, g):
     methods = [choose_method(int(h), int(w), r, r) for h, w in rows[:, 3:5]]
     mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
     smp = ops.Sampler(r, patch, cuda_device, mean, std)
