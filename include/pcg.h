@@ -153,6 +153,18 @@ int pcg_head_loss(const float *x, const float *ln_g, const float *ln_b, const fl
                   float *loss_sum, float *enc_out, const float *d_enc, float *dx, void *dx_bf16, float *workspace,
                   void *stream);
 
+/* ---- guided-sampling glue ----------------------------------------------------------------
+ * out[n,i] = a[n] x[n,i] + b[n] clamp(y[n,i], -clamp_limit, clamp_limit) + c[n];  coef = f32 [3][n_samples] (a,b,c)
+ * on the device, y nullable (then b is ignored), clamp_limit = INFINITY for no clamp.  With coefficients from
+ * alpha = cos(t pi/2), sigma = sin(t pi/2) this is Predictions.denoised_images / .step(eta=0) / .guided and their
+ * backward (perceptor/models/velocity_diffusion/predictions.py:50-66,68-105,148-155; diffusion_space.py:1-6). */
+int pcg_affine2(const float *x, const float *y, const float *coef, float *out, int n_samples, long long per,
+                float clamp_limit, void *stream);
+/* g == NULL: out = clamp(x, lo, hi).  g != NULL: out = g * [g (x - clamp(x, lo, hi)) >= 0], the backward of
+ * clamp_with_grad (perceptor/transforms/clamp_with_grad.py:8-27). */
+int pcg_clamp_with_grad(const float *x, const float *g, float *out, long long total, float lo, float hi,
+                        void *stream);
+
 /* ---- whole path ------------------------------------------------------------------------------------------ */
 /* bytes of scratch (transient) and stash (activations kept for backward) for n cutouts. */
 size_t pcg_workspace_bytes(const pcg_vit_config *cfg, int n_cut);

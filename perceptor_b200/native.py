@@ -94,6 +94,8 @@ SIGNATURES = {
     "pcg_stash_bytes": (C.c_size_t, [C.POINTER(VitConfig), _i]),
     "pcg_guidance_fwd": (_i, [C.POINTER(GuidanceArgs), _vp]),
     "pcg_guidance_bwd": (_i, [C.POINTER(GuidanceArgs), _vp]),
+    "pcg_affine2": (_i, [_vp, _vp, _vp, _vp, _i, C.c_longlong, _f, _vp]),
+    "pcg_clamp_with_grad": (_i, [_vp, _vp, _vp, C.c_longlong, _f, _f, _vp]),
     "pcg_profile_enable": (_i, [_i]),
     "pcg_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }

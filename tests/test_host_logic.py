@@ -152,3 +152,29 @@ def test_module_surface_and_error_behaviour_without_gpu(tmp_path):
     raw = torch.randn(2, 512) * 3
     oc.add_encodings_(raw)
     assert torch.allclose(oc.encodings, raw)  # OpenCLIP stores targets as given
+
+
+def test_schedule_ts_and_glue_host_logic_match_reference_golden():
+    """schedule_ts is host arithmetic: bit-equal to the reference's VelocityDiffusion.schedule_ts output."""
+    from pathlib import Path
+
+    from perceptor_b200 import utils, velocity_diffusion as vd
+
+    z = np.load(Path(__file__).parent / "golden" / "diffusion_glue.npz")
+    assert np.array_equal(vd.schedule_ts(50).numpy(), z["schedule_50"])
+    assert np.array_equal(vd.schedule_ts(7, 0.9, 0.05, 5.0).numpy(), z["schedule_7"])
+    rows = vd.schedule_ts(n_steps=50)
+    assert rows.shape == (50, 2) and bool((rows[:, 0] > rows[:, 1]).all()) and torch.equal(rows[1:, 0], rows[:-1, 1])
+    # no CPU fallback for the fused maps
+    p = vd.Predictions(torch.rand(1, 3, 4, 4), torch.tensor([0.5]), torch.randn(1, 3, 4, 4))
+    with pytest.raises(RuntimeError):
+        _ = p.denoised_images
+    with pytest.raises(ValueError):
+        p.alphas(torch.zeros(2, 2))
+    # gradient_checkpoint (perceptor/utils/gradient_checkpoint.py:71-79, the reference's own test)
+    images = torch.zeros(1, 3, 8, 8).requires_grad_()
+    checkpoint = utils.gradient_checkpoint(images * 2)
+    checkpoint.tensor().pow(2).add(checkpoint.tensor()).mean().backward()
+    assert checkpoint.detached.grad is not None
+    checkpoint.continue_backward()
+    assert images.grad is not None and torch.allclose(images.grad, torch.full_like(images, 2.0 / images.numel()))

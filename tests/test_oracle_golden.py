@@ -90,3 +90,31 @@ def test_sampler_rows_match_golden():
         seed, b, h, w, n, lo, hi = (int(v) for v in z[f"args{j}"])
         rows = sampler_oracle.sample_cutouts(torch.Generator().manual_seed(seed), b, h, w, n, float(z[f"pow{j}"]), lo, hi)
         assert np.array_equal(np.array(rows, dtype=np.int32), z[f"rows{j}"])
+
+
+def test_diffusion_glue_matches_reference_predictions():
+    """oracle/diffusion.py against vectors from the reference's own predictions.py / velocity_diffusion.py /
+    clamp_with_grad.py (oracle/make_golden_diffusion.py)."""
+    from oracle import diffusion as dz
+
+    z = np.load(GOLDEN / "diffusion_glue.npz")
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    assert np.array_equal(dz.schedule_ts(50).numpy(), z["schedule_50"])
+    assert np.array_equal(dz.schedule_ts(7, 0.9, 0.05, 5.0).numpy(), z["schedule_7"])
+    args = (t["images"], t["ts"], t["velocities"])
+    for name, got in [("denoised_xs", dz.denoised_xs(*args)), ("predicted_noise", dz.predicted_noise(*args)),
+                      ("denoised_images", dz.denoised_images(*args)), ("step", dz.step(*args, t["to_ts"])),
+                      ("guided", dz.guided(*args, t["guiding"], 0.7, 1e-6)),
+                      ("forced", dz.forced_denoised_images(*args, t["images"].flip(0)))]:
+        assert torch.equal(got, t[name]), name  # the same float32 expressions: bit-equal
+    v, x = t["velocities"].clone().requires_grad_(), t["images"].clone().requires_grad_()
+    gv, gx = torch.autograd.grad((dz.denoised_images(x, t["ts"], v) * t["cot"]).sum(), (v, x))
+    assert torch.equal(gv, t["grad_velocities"]) and torch.equal(gx, t["grad_images"])
+    one = (t["images"][:1], t["ts"][:1], t["velocities"][:1] * 3)
+    assert torch.allclose(dz.dynamic_threshold_velocities(*one, 0.9), t["dynamic_threshold"], atol=1e-6)
+    static = dz.forced_denoised_images(*one, dz.clamp_with_grad(dz.denoised_images(*one), 0, 1))
+    assert torch.allclose(static, t["static_threshold"], atol=1e-6)
+    zz = t["cwg_x"].clone().requires_grad_()
+    y = dz.clamp_with_grad(zz, 0.0, 1.0)
+    (gz,) = torch.autograd.grad(y, zz, t["cwg_gin"])
+    assert torch.equal(y.detach(), t["cwg_y"]) and torch.equal(gz, t["cwg_gx"])
