@@ -212,7 +212,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         loss = loss_mod(img)
         loss.backward()
         host_grad.copy_(img.grad, non_blocking=True)
-        return float(loss)  # D2H read of the scalar; synchronises the step
+        return float(loss.detach())  # D2H read of the scalar; synchronises the step
 
     def barrier():
         if world > 1:
