@@ -94,7 +94,8 @@ class _TextImageLoss(torch.nn.Module):
 
 class CLIP(_TextImageLoss):
     def __init__(self, name="ViT-B-32", precision="fp32", jit=False, *, n_cutouts=None, cut_pow=1.0, min_size=None,
-                 max_size=None, seed=0, generator=None, process_group=None, state_dict=None, weights_seed=0):
+                 max_size=None, seed=0, generator=None, process_group=None, state_dict=None, weights_seed=0,
+                 bpe_path=None):
         """
         Args:
             name: name of the clip model. Available models on the native path:
@@ -106,7 +107,7 @@ class CLIP(_TextImageLoss):
         super().__init__()
         self.name = name
         extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
-        self.model = models.CLIP(name, precision, **extra)
+        self.model = models.CLIP(name, precision, bpe_path=bpe_path, **extra)
         self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group)
         self.multiplier = 0.01 if name in ("ViT-L-14", "ViT-L-14-336") else 1.0
 
@@ -129,7 +130,7 @@ class OpenCLIP(_TextImageLoss):
 
     def __init__(self, architecture="ViT-L-14", weights="laion2b_s32b_b82k", *, n_cutouts=None, cut_pow=1.0,
                  min_size=None, max_size=None, seed=0, generator=None, process_group=None, state_dict=None,
-                 weights_seed=0):
+                 weights_seed=0, bpe_path=None):
         """
         Args:
             architecture (str): name of the clip model
@@ -140,8 +141,79 @@ class OpenCLIP(_TextImageLoss):
         super().__init__()
         self.architecture = architecture
         extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
-        self.model = models.OpenCLIP(architecture, weights, **extra)
+        self.model = models.OpenCLIP(architecture, weights, bpe_path=bpe_path, **extra)
         self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group)
 
     def forward(self, images):
         return self._loss(images, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# other consumers of the same image encoder: the native path ends at `encode_images`, whose
+# autograd.Function takes an arbitrary upstream gradient; the heads below are a few dozen FLOPs of torch on [N, E].
+# ---------------------------------------------------------------------------------------------------------
+class SphericalDistance(torch.nn.Module):
+    """perceptor/losses/spherical_distance.py:4-21: mean pairwise 2 asin(|a - b| / 2)^2 between two image batches."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, images_a, images_b):
+        enc_a, enc_b = self.model.encode_images(images_a), self.model.encode_images(images_b)
+        return (enc_a[:, None] - enc_b[None, :]).norm(dim=2).div(2).arcsin().square().mul(2).mean()
+
+
+class SimulacraAesthetic(torch.nn.Module):
+    """perceptor/losses/simulacra_aesthetic.py:8-44 over perceptor/models/simulacra_aesthetic/simulacra_aesthetic.py:
+    26-60: a linear probe on sqrt(E) * normalised CLIP encodings predicts the rating; loss = multiplier * mse to the
+    target.  The probe's checkpoint cannot be downloaded offline: pass `head_state_dict` ({"linear.weight",
+    "linear.bias"}) or get a random-init probe."""
+
+    def __init__(self, model_name="ViT-L-14", aesthetic_target=10, *, head_state_dict=None, state_dict=None,
+                 weights_seed=0):
+        super().__init__()
+        self.aesthetic_target = torch.nn.Parameter(torch.as_tensor(aesthetic_target).float(), requires_grad=False)
+        extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
+        self.clip_model = models.CLIP(model_name, **extra)
+        self.linear = torch.nn.Linear(self.clip_model.shape.embed, 1)
+        if head_state_dict is not None:
+            self.linear.load_state_dict({k.replace("linear.", ""): v for k, v in head_state_dict.items()})
+        self.linear.eval().requires_grad_(False)
+        self.linear.to(self.clip_model.device)
+        self.multiplier = 0.00001 if model_name in ("ViT-L-14", "ViT-L-14-336") else 0.001
+
+    def predict(self, images):
+        encodings = self.clip_model.encode_images(images)
+        return self.linear(F.normalize(encodings, dim=-1) * encodings.shape[-1] ** 0.5)
+
+    def forward(self, images):
+        return self.multiplier * F.mse_loss(self.predict(images), self.aesthetic_target.view(-1, 1).to(self.linear.weight))
+
+
+class AestheticVisualAssessment(torch.nn.Module):
+    """perceptor/losses/aesthetic_visual_assessment.py:10-51: a 10-way rating classifier on ViT-B/16 encodings."""
+
+    def __init__(self, aesthetic_target=10, mode="expected", *, head_state_dict=None, state_dict=None, weights_seed=0):
+        super().__init__()
+        self.aesthetic_target = aesthetic_target
+        self.mode = mode
+        extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
+        self.model = models.CLIP("ViT-B-16", **extra)
+        self.aesthetic_head = torch.nn.Linear(512, 10)
+        if head_state_dict is not None:
+            self.aesthetic_head.load_state_dict(head_state_dict)
+        self.aesthetic_head.eval().requires_grad_(False)
+        self.aesthetic_head.to(self.model.device)
+
+    def forward(self, images):
+        log_probs = self.aesthetic_head(self.model.encode_images(images))
+        if self.mode == "logit":
+            return -log_probs[..., self.aesthetic_target - 1].mean().mul(0.01)
+        elif self.mode == "expected":
+            expected_target = F.softmax(log_probs, dim=-1) * torch.arange(10).add(1).to(log_probs.device)
+            return (expected_target - self.aesthetic_target).square().mean().mul(0.01)
+        elif self.mode == "probability":
+            return -F.softmax(log_probs, dim=-1)[..., self.aesthetic_target - 1].mean()
+        else:
+            raise ValueError(f"Unknown mode: {self.mode}")

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import cutouts, native
+from . import checkpoints, cutouts, native, text
 from .guidance import EncodeImagesFn, GuidanceEngine
 from .vit import random_state_dict, required_keys, resolve_shape
 
@@ -28,8 +28,13 @@ _PRETRAINED = {
 
 
 class _OpenCLIP(torch.nn.Module):
-    def __init__(self, architecture="ViT-L-14", weights="openai", precision=None, *, state_dict=None, seed=0):
+    def __init__(self, architecture="ViT-L-14", weights="openai", precision=None, *, state_dict=None, seed=0,
+                 bpe_path=None):
         super().__init__()
+        self._bpe_path = bpe_path
+        self._seed = int(seed)
+        self._tokenizer = None
+        self._text_sd = None
         self.architecture = architecture
         self.weights = weights
         if (architecture, weights) not in _PRETRAINED:
@@ -41,8 +46,11 @@ class _OpenCLIP(torch.nn.Module):
         self.name, self.shape = resolve_shape(architecture)
         quick = weights == "openai" or "-quickgelu" in architecture
         self.act = native.ACT_QUICKGELU if quick else native.ACT_GELU
-        sd = state_dict if state_dict is not None else random_state_dict(self.shape, seed)
-        sd = {k[len("visual."):] if k.startswith("visual.") else k: v for k, v in sd.items()}
+        # OpenAI / open_clip / Hugging Face layouts -> OpenAI vision names (+ "text.*" when the text tower is there)
+        sd = checkpoints.normalize_state_dict(state_dict) if state_dict is not None else random_state_dict(self.shape, seed)
+        self._text_shape = text.TEXT_SHAPES[self.name]
+        if all("text." + k in sd for k in text.text_keys(self._text_shape.layers)):
+            self._text_sd = {k: sd["text." + k].detach().float() for k in text.text_keys(self._text_shape.layers)}
         missing = [k for k in required_keys(self.shape.layers) if k not in sd]
         if missing:
             raise ValueError(f"state_dict is missing vision keys: {missing[:4]}...")
@@ -67,10 +75,21 @@ class _OpenCLIP(torch.nn.Module):
     def state_dict_openai(self) -> dict[str, torch.Tensor]:
         return {k: getattr(self, k.replace(".", "__")).detach() for k in self._keys}
 
+    @torch.no_grad()
     def encode_texts(self, text_prompts, normalize=True):
-        raise NotImplementedError(
-            "the text tower is outside the accelerated hot path (SURVEY.md §8f-2); pass precomputed text "
-            "encodings to add_encodings_()")
+        """perceptor/models/open_clip.py:99-107: tokenize -> text transformer -> (L2-normalise).  Plain PyTorch on
+        the encoder's device (once per prompt).  Needs the CLIP BPE merge table: `bpe_path=` at
+        construction or PCG_BPE_VOCAB.  Without a checkpoint the text tower is random-init like the image tower."""
+        if self._tokenizer is None:
+            self._tokenizer = text.SimpleTokenizer(self._bpe_path)
+        if self._text_sd is None:
+            self._text_sd = text.random_text_state_dict(self._text_shape, self._seed + 1)
+        dev = self.device
+        if next(iter(self._text_sd.values())).device != dev:
+            self._text_sd = {k: v.to(dev) for k, v in self._text_sd.items()}
+        tokens = text.tokenize(self._tokenizer, text_prompts, self._text_shape.context)
+        encodings = text.encode_text(self._text_sd, self._text_shape, tokens, quick_gelu=self.act == native.ACT_QUICKGELU)
+        return F.normalize(encodings) if normalize else encodings
 
     def engine(self) -> GuidanceEngine:
         dev = self.device
@@ -107,14 +126,14 @@ class _OpenCLIP(torch.nn.Module):
 _cache: "weakref.WeakValueDictionary[str, _OpenCLIP]" = weakref.WeakValueDictionary()
 
 
-def OpenCLIP(architecture="ViT-L-14", weights="openai", precision=None, *, state_dict=None, seed=0):
+def OpenCLIP(architecture="ViT-L-14", weights="openai", precision=None, *, state_dict=None, seed=0, bpe_path=None):
     """Weak-valued memoised constructor (perceptor/utils/cache.py:9-23): equal arguments share one encoder."""
     if state_dict is not None:
-        return _OpenCLIP(architecture, weights, precision, state_dict=state_dict)
-    key = str((architecture, weights, precision, int(seed)))
+        return _OpenCLIP(architecture, weights, precision, state_dict=state_dict, bpe_path=bpe_path)
+    key = str((architecture, weights, precision, int(seed), bpe_path))
     model = _cache.get(key)
     if model is None:
-        model = _OpenCLIP(architecture, weights, precision, seed=seed)
+        model = _OpenCLIP(architecture, weights, precision, seed=seed, bpe_path=bpe_path)
         _cache[key] = model
     return model
 

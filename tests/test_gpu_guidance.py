@@ -171,3 +171,67 @@ def test_full_size_properties_config2(cuda_device):
     assert abs(sum(p[0] for p in parts) - full_loss) <= 1e-4 * abs(full_loss)
     assert cosine(parts[0][1] + parts[1][1], full_grad) >= 0.9999
     assert float(full_grad.abs().sum()) > 0 and torch.isfinite(full_grad).all()
+
+
+def _ref_encode(images, model, rows=None):
+    """CPU oracle encodings of whole images with the weights of a models.CLIP instance"""
+    sd = {k: v.detach().cpu() for k, v in model.state_dict_openai().items()}
+    s = model.shape
+    rows = rows if rows is not None else cutouts.whole_image_cutouts(images.shape[0], images.shape[2], images.shape[3]).tolist()
+    return guidance_oracle.encode_cutouts(images, rows, sd, s.image_size, s.patch, s.layers, s.heads)
+
+
+def test_other_consumers_of_the_encoder(cuda_device):
+    """§8f-4: SphericalDistance and the aesthetic heads run on the native encode_images and back-propagate to the
+    images; each is compared with the same head on the CPU oracle's encodings."""
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(2, 3, 96, 80, generator=g), torch.rand(1, 3, 64, 64, generator=g)
+    sim = losses.SimulacraAesthetic("ViT-B-32", aesthetic_target=7)
+    model = sim.clip_model
+    dist = losses.SphericalDistance(model)
+    xa, xb = a.to(cuda_device).requires_grad_(), b.to(cuda_device).requires_grad_()
+    d = dist(xa, xb)
+    d.backward()
+    ra, rb = a.clone().requires_grad_(), b.clone().requires_grad_()
+    d_ref = (_ref_encode(ra, model)[:, None] - _ref_encode(rb, model)[None, :]).norm(dim=2).div(2).arcsin().square().mul(2).mean()
+    d_ref.backward()
+    assert abs(float(d) - float(d_ref)) <= LOSS_RTOL * abs(float(d_ref))
+    assert cosine(xa.grad.cpu(), ra.grad) >= GRAD_COS and cosine(xb.grad.cpu(), rb.grad) >= GRAD_COS
+
+    xa2 = a.to(cuda_device).requires_grad_()
+    s = sim(xa2)
+    s.backward()
+    ra2 = a.clone().requires_grad_()
+    enc = _ref_encode(ra2, model)
+    lin = torch.nn.Linear(512, 1)
+    lin.load_state_dict({k: v.cpu() for k, v in sim.linear.state_dict().items()})
+    s_ref = 0.001 * torch.nn.functional.mse_loss(lin(torch.nn.functional.normalize(enc, dim=-1) * 512**0.5),
+                                                 torch.tensor(7.0).view(-1, 1).expand(2, 1))
+    s_ref.backward()
+    assert abs(float(s) - float(s_ref)) <= LOSS_RTOL * abs(float(s_ref))
+    assert cosine(xa2.grad.cpu(), ra2.grad) >= GRAD_COS
+
+    for mode in ("logit", "expected", "probability"):
+        ava = losses.AestheticVisualAssessment(aesthetic_target=8, mode=mode)
+        x = b.to(cuda_device).requires_grad_()
+        v = ava(x)
+        v.backward()
+        assert v.dim() == 0 and torch.isfinite(x.grad).all() and float(x.grad.abs().sum()) > 0
+    with pytest.raises(ValueError):
+        losses.AestheticVisualAssessment(mode="nope")(b.to(cuda_device))
+
+
+def test_add_texts_through_the_module_api(cuda_device, tmp_path):
+    """§8f-2: add_texts_ tokenizes and runs the text tower (random-init offline) -- here on a toy merge table."""
+    import gzip
+
+    path = tmp_path / "toy_vocab.txt.gz"
+    with gzip.open(path, "wb") as f:
+        f.write(b"#version: toy\nl o\nlo w</w>\n")
+    loss = losses.CLIP("ViT-B-32", n_cutouts=2, min_size=32, bpe_path=str(path))
+    loss.add_texts_(["low", "a low wall"], weights=[1.0, -0.5])
+    assert loss.encodings.shape == (2, 512) and loss.encodings.device.type == "cuda"
+    assert torch.allclose(loss.encodings.norm(dim=1), torch.ones(2, device=loss.device), atol=1e-5)
+    x = torch.rand(1, 3, 64, 64, device=cuda_device).requires_grad_()
+    loss(x).backward()
+    assert torch.isfinite(x.grad).all()

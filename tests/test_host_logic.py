@@ -142,7 +142,7 @@ def test_module_surface_and_error_behaviour_without_gpu(tmp_path):
     # no CPU fallback: the image path must fail loudly off-GPU
     with pytest.raises(RuntimeError):
         loss(torch.rand(1, 3, 64, 64))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError, match="merge table"):  # the BPE vocabulary is user-supplied data
         loss.add_texts_(["hello"])
     stub = tmp_path / "textoff.json"
     stub.write_text('{"ViT-B-32": [[0.1, 0.2]]}')
