@@ -487,6 +487,200 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// forward, long sequences (T - 1 > 256: ViT-L/14 @336 has 576 + 1 tokens)
+// ---------------------------------------------------------------------------------------------------------
+// Same CTA shape as above (cutout, head, 128-query tile; 2 CTAs / SM), but S no longer fits tensor memory, so the
+// keys stream through a two-stage ring of 128-row K / V blocks with the online softmax: per chunk
+//   S_c = Q K_c^T  ->  m' = max(m, rowmax S_c),  P_c = exp2(S_c - m') over the dead S columns,
+//   l = l alpha + rowsum P_c,  O = O alpha (tcgen05.ld / st on the 64 accumulator columns, alpha = exp2(m - m'))
+//   ->  O += P_c V_c (A = P_c from TMEM).
+// The MMAs of one chunk and the softmax of the same chunk are serial inside a CTA; the second CTA of the SM fills
+// the gaps.  The edge key (token T - 1) enters as the initial maximum and in the epilogue exactly as above; the
+// edge QUERY row is left to the mma.sync kernel (one row per head: it would need every K / V chunk a second time).
+constexpr int kFlashOffBar = kFwdOffX + 512;  // float k_x[64], v_x[64]; then 8 mbarriers + tmem slot
+constexpr int kFlashSmemBytes = kFlashOffBar + 128 + 1024;
+constexpr uint32_t kFlashColO = 128;
+enum { kFbK = 0, kFbV = 2, kFbS = 4, kFbP = 5, kFbO = 6, kFbX = 7 };
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sm_k = sm;             // two stages of [128 keys x 64]
+    uint8_t* sm_v = sm + kFwdOffV;  // two stages
+    uint8_t* sm_q = sm + kFwdOffQ;
+    float* kx = reinterpret_cast<float*>(sm + kFwdOffX);
+    float* vx = kx + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kFlashOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+    const int D = p.heads * kHd, nv = p.nv;
+    const int q0 = tile * 128;
+    const int nc = (nv + 127) >> 7;
+    const size_t cta_id = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+
+    uint32_t xk = 0, xv = 0;
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(&bars[kFbK], 1);
+            mbar_init(&bars[kFbK + 1], 1);
+            mbar_init(&bars[kFbV], 1);
+            mbar_init(&bars[kFbV + 1], 1);
+            mbar_init(&bars[kFbS], 1);
+            mbar_init(&bars[kFbP], 4);
+            mbar_init(&bars[kFbO], 1);
+            mbar_init(&bars[kFbX], 1);
+            fence_barrier_init();
+            if (cta_id < static_cast<size_t>(p.stagger_ctas)) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                if (atomicAdd(&g_fwd_sm_arrivals[smid & 1023], 1u) & 1u) {
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < p.stagger_cycles) {
+                    }
+                }
+            }
+            mbar_arrive_expect_tx(&bars[kFbK], 2 * kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[kFbK], sm_q, h * kHd, q0, n, kEvictFirst);
+            tma_load_3d(&map_qkv, &bars[kFbK], sm_k, D + h * kHd, 0, n, kEvictNormal);
+            mbar_arrive_expect_tx(&bars[kFbV], kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[kFbV], sm_v, 2 * D + h * kHd, 0, n, kEvictNormal);
+            if (nc > 1) {
+                mbar_arrive_expect_tx(&bars[kFbK + 1], kBlkBytes);
+                tma_load_3d(&map_qkv, &bars[kFbK + 1], sm_k + kBlkBytes, D + h * kHd, 128, n, kEvictNormal);
+                mbar_arrive_expect_tx(&bars[kFbV + 1], kBlkBytes);
+                tma_load_3d(&map_qkv, &bars[kFbV + 1], sm_v + kBlkBytes, 2 * D + h * kHd, 128, n, kEvictNormal);
+            }
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    } else if (warp == 5) {
+        const bf16* xrow_g = p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd + 2 * lane;
+        xk = *reinterpret_cast<const uint32_t*>(xrow_g + D);
+        xv = *reinterpret_cast<const uint32_t*>(xrow_g + 2 * D);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+            for (int c = 0; c < nc; ++c) {
+                const int st = c & 1;
+                const uint32_t ph = (c >> 1) & 1;
+                mbar_wait(&bars[kFbK + st], ph);
+                tc_fence_after();
+                // S_c (it queues behind P_{c-1} V_{c-1}, which reads the columns it overwrites: same pipe, in order)
+                mma_tile_x_rows(tmem, sm_q, sm_k + st * kBlkBytes, 128);
+                umma_commit(&bars[kFbS]);
+                if (c >= 1 && c + 1 < nc) {
+                    // the other stage held chunk c - 1: its K block was consumed by S_{c-1} (done before P_{c-1} was
+                    // signalled), its V block is free once P_{c-1} V_{c-1} has retired
+                    const int s2 = st ^ 1;
+                    mbar_arrive_expect_tx(&bars[kFbK + s2], kBlkBytes);
+                    tma_load_3d(&map_qkv, &bars[kFbK + s2], sm_k + s2 * kBlkBytes, D + h * kHd, (c + 1) * 128, n, kEvictNormal);
+                    mbar_wait(&bars[kFbO], (c - 1) & 1);
+                    mbar_arrive_expect_tx(&bars[kFbV + s2], kBlkBytes);
+                    tma_load_3d(&map_qkv, &bars[kFbV + s2], sm_v + s2 * kBlkBytes, 2 * D + h * kHd, (c + 1) * 128, n, kEvictNormal);
+                }
+                mbar_wait(&bars[kFbV + st], ph);
+                mbar_wait(&bars[kFbP], c & 1);
+                tc_fence_after();
+                const int ksteps = min(8, (nv - c * 128 + 15) >> 4);
+                for (int ks = 0; ks < ksteps; ++ks)
+                    umma_f16_ts(tmem + kFlashColO, tmem + ks * 8,
+                                umma_smem_desc_sw128(smem_u32(sm_v + st * kBlkBytes + ks * 2048)), idesc_pv, c > 0 || ks != 0);
+                umma_commit(&bars[kFbO]);
+            }
+        }
+    } else if (warp < 4) {
+        const int r = warp * 32 + lane;
+        const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        mbar_wait(&bars[kFbX], 0);
+        mbar_wait(&bars[kFbK], 0);
+        const float sx = row_dot(sm_q, r, kx);  // score against the edge key
+        float mx = sx, sum = 0.f;
+        for (int c = 0; c < nc; ++c) {
+            const int nvl = min(128, nv - c * 128);  // valid keys of this chunk
+            const int cend = (nvl + 31) & ~31;
+            mbar_wait(&bars[kFbS], c & 1);
+            tc_fence_after();
+            const float m_new = fwd_row_max(trow, cend, nvl, mx);
+            const float alpha = exp2f((mx - m_new) * kLog2e);
+            mx = m_new;
+            sum = fwd_row_exp(trow, 0, cend, 0, nvl, m_new * kLog2e, sum * alpha);
+            if (c > 0) {
+                mbar_wait(&bars[kFbO], (c - 1) & 1);  // O holds chunks 0 .. c-1 (already true: S_c was issued after them)
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t o[32];
+                        tmem_ld<32>(trow + kFlashColO + 32 * hh, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+                        tmem_st<16>(trow + kFlashColO + 32 * hh, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                        tmem_st<16>(trow + kFlashColO + 32 * hh + 16, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                    }
+                }
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kFbP]);
+        }
+        const float px = exp2f((sx - mx) * kLog2e);
+        sum += px;
+        if (q0 + r < nv) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + q0 + r] = mx + logf(sum);
+        const float inv = 1.0f / sum;
+        mbar_wait(&bars[kFbO], (nc - 1) & 1);
+        tc_fence_after();
+        uint32_t v[64];
+        tmem_ld_32x32(trow + kFlashColO, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+        tmem_ld_32x32(trow + kFlashColO + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float4 xa = *reinterpret_cast<const float4*>(vx + g * 8);
+            const float4 xb = *reinterpret_cast<const float4*>(vx + g * 8 + 4);
+            const uint4 o = make_uint4(pack_bf16(fmaf(px, xa.x, __uint_as_float(v[8 * g])) * inv,
+                                                 fmaf(px, xa.y, __uint_as_float(v[8 * g + 1])) * inv),
+                                       pack_bf16(fmaf(px, xa.z, __uint_as_float(v[8 * g + 2])) * inv,
+                                                 fmaf(px, xa.w, __uint_as_float(v[8 * g + 3])) * inv),
+                                       pack_bf16(fmaf(px, xb.x, __uint_as_float(v[8 * g + 4])) * inv,
+                                                 fmaf(px, xb.y, __uint_as_float(v[8 * g + 5])) * inv),
+                                       pack_bf16(fmaf(px, xb.z, __uint_as_float(v[8 * g + 6])) * inv,
+                                                 fmaf(px, xb.w, __uint_as_float(v[8 * g + 7])) * inv));
+            *reinterpret_cast<uint4*>(sm_q + row_chunk(r, g)) = o;
+        }
+        __syncwarp();
+        bf16* gout = p.out + static_cast<size_t>(n) * p.T * D + h * kHd;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = warp * 32 + i * 4 + (lane >> 3), ch = lane & 7;
+            if (q0 + row < nv)
+                *reinterpret_cast<uint4*>(gout + static_cast<size_t>(q0 + row) * D + ch * 8) =
+                    *reinterpret_cast<const uint4*>(sm_q + row_chunk(row, ch));
+        }
+    } else {
+        kx[2 * lane] = bf_lo(xk), kx[2 * lane + 1] = bf_hi(xk);
+        vx[2 * lane] = bf_lo(xv), vx[2 * lane + 1] = bf_hi(xv);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[kFbX]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 384;  // warps 0-7 elementwise (lane quarter = warp & 3, column phase = warp >> 2),
@@ -935,8 +1129,10 @@ int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols) {
     return 0;
 }
 
-// tensor-core path: T - 1 tokens in one or two 128-row tiles, at least 65 so the tile is not mostly padding
+// tensor-core path: at least 65 tokens beside the edge token so that a 128-row tile is not mostly padding.
+// T - 1 <= 256: everything in tensor memory at once (forward) / one fused backward; beyond that the streaming forward.
 bool use_tc(int T) { return T >= 66 && T <= 257; }
+bool use_flash_fwd(int T) { return T > 257; }
 
 long long* g_trace = nullptr;
 int g_fwd_stagger = []() {
@@ -970,10 +1166,23 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "pcg_attn_fwd: n and heads must be <= 65535");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ProfileScope prof(PCG_PROF_ATTN_FWD, 4.0 * T * T * kHd * heads * n, s);
-    if (g_force_legacy || !use_tc(T)) return attn_fwd_legacy(qkv, out, lse, n, T, heads, 0, s);
+    if (g_force_legacy || !(use_tc(T) || use_flash_fwd(T))) return attn_fwd_legacy(qkv, out, lse, n, T, heads, 0, s);
     const int D = heads * kHd;
     CUtensorMap map;
     if (int rc = make_map3(&map, qkv, n, T, 3 * D)) return rc;
+    if (use_flash_fwd(T)) {
+        static bool flash_configured = false;
+        if (!flash_configured) {
+            PCG_CUDA(cudaFuncSetAttribute(attn_fwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlashSmemBytes));
+            flash_configured = true;
+        }
+        const int nvf = T - 1;
+        FwdParams pf{T, heads, nvf, (nvf + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
+                     nullptr, 2 * sm_count(), g_fwd_stagger};
+        attn_fwd_flash_kernel<<<dim3((nvf + 127) / 128, heads, n), kFwdThreads, kFlashSmemBytes, s>>>(map, pf);
+        PCG_LAUNCH_CHECK("attn_fwd_flash_kernel");
+        return attn_fwd_legacy(qkv, out, lse, n, T, heads, nvf, s);  // the edge query row
+    }
     static bool configured = false;
     if (!configured) {
         PCG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
