@@ -10,7 +10,9 @@ perceptor/models/open_clip.py:109-123) and the autograd tape behind them.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
+import os
+import weakref
+from dataclasses import dataclass, replace
 
 import numpy as np
 import torch
@@ -33,6 +35,39 @@ class CutPlan:
     tab_tensors: tuple        # keep-alive
 
 
+class _GraphSlot:
+    """Static buffers + the two captured CUDA graphs of one (shape, cutout count) configuration of the loss path.
+
+    The guidance step is ~390 dependent launches; replaying them from a graph removes the launch gaps between them
+    (ViT-L/14 x 128 cutouts: 53.7 -> 51.3 ms, ViT-B/32 x 256: 8.3 -> 7.8 ms on B200).  Everything a launch reads or
+    writes lives in buffers owned by the slot; a call copies its inputs in (a few MB) and clones its outputs out."""
+
+    def __init__(self, engine: "GuidanceEngine", images, plan: CutPlan, targets, tweights):
+        dev = engine.device
+        self.images = torch.empty_like(images)
+        self.table = torch.empty_like(plan.table)
+        self.targets = torch.empty_like(targets)
+        self.tweights = torch.empty_like(tweights)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.d_images = torch.zeros_like(images)
+        self.stash = torch.empty(engine.stash_bytes(plan.n_local), dtype=torch.uint8, device=dev)
+        self.fwd_graph: torch.cuda.CUDAGraph | None = None
+        self.bwd_graph: torch.cuda.CUDAGraph | None = None
+        self.calls_fwd = 0
+        self.calls_bwd = 0
+        # weak reference to the token of the forward whose activations the stash holds; it dies with that forward's
+        # autograd node, so a loss that is never back-propagated does not pin the slot
+        self.owner: weakref.ref | None = None
+        self.launches_fwd = self.launches_bwd = 0
+
+    def busy(self) -> bool:
+        return self.owner is not None and self.owner() is not None
+
+
+class _Token:
+    __slots__ = ("__weakref__",)
+
+
 class GuidanceEngine:
     """Owns packed weights, resize tables and scratch memory for one encoder on one device."""
 
@@ -49,6 +84,11 @@ class GuidanceEngine:
         self._workspace: torch.Tensor | None = None
         self.launches_fwd = 0
         self.launches_bwd = 0
+        # CUDA-graph replay of the loss path (PCG_CUDA_GRAPHS=0 turns it off); one slot is kept at a time
+        self.use_graphs = os.environ.get("PCG_CUDA_GRAPHS", "1") != "0"
+        self._slot_key = None
+        self._slot: _GraphSlot | None = None
+        self._prebuilt_side = 0
 
     # ------------------------------------------------------------------ plans
     def _method_for_size(self, s: int) -> int:
@@ -149,6 +189,103 @@ class GuidanceEngine:
         self.launches_bwd = lib.pcg_last_launch_count()
         return d_images
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the loss path
+    def _slot_for(self, images, plan: CutPlan, targets, tweights, loss_scale: float):
+        """The graph slot matching this call, (re)built when the configuration changes; None when graphs do not apply."""
+        if not self.use_graphs or plan.n_local == 0 or torch.cuda.is_current_stream_capturing():
+            return None
+        ws = self._get_workspace(plan.n_local)
+        # graphs bake the resize-table pointers in: build every table a crop of this image can need up front, so that
+        # the device copy is uploaded once and never moves (table ids are append-only, older plans stay valid)
+        side = int(max(images.shape[2], images.shape[3]))
+        if side > self._prebuilt_side:
+            self.prebuild_tables(1, side)
+            self._prebuilt_side = side
+        tabs = self.tables.device_tensors(self.device)
+        key = (tuple(images.shape), plan.n_local, plan.n_total, tuple(targets.shape), float(loss_scale),
+               tuple(t.data_ptr() for t in tabs), ws.data_ptr())
+        if key != self._slot_key:
+            self._slot = None  # frees the previous slot's stash before the new one is allocated
+            self._slot_key = None
+            self._slot = _GraphSlot(self, images, plan, targets, tweights)
+            self._slot_key = key
+        slot = self._slot
+        if slot.busy():  # a forward is still waiting for its backward: do not clobber its activations
+            return None
+        return slot
+
+    def _slot_plan(self, slot: _GraphSlot, plan: CutPlan, width: int) -> CutPlan:
+        # the sampler's launch geometry depends on the widest crop: fix it at the image width so one graph fits all;
+        # the resize tables are the engine's complete, pinned-in-place set
+        tabs = self.tables.device_tensors(self.device)
+        tabs_c = native.ResizeTables(desc=tabs[0].data_ptr(), left=tabs[1].data_ptr(), weight=tabs[2].data_ptr(),
+                                     inv=tabs[3].data_ptr(), n_desc=tabs[0].shape[0])
+        return replace(plan, table=slot.table, max_in_w=int(width), tabs_c=tabs_c, tab_tensors=tabs)
+
+    def forward_graphed(self, slot: _GraphSlot, images, plan: CutPlan, targets, tweights, loss_scale: float, token):
+        """Loss forward (activations kept) through the slot.  The first call runs eagerly on the static buffers, the
+        second captures, later ones replay."""
+        self._check_images(images)
+        lib = native.lib()
+        slot.images.copy_(images)
+        slot.table.copy_(plan.table)
+        slot.targets.copy_(targets)
+        slot.tweights.copy_(tweights)
+        splan = self._slot_plan(slot, plan, images.shape[3])
+        ws = self._get_workspace(plan.n_local)
+
+        def launch():
+            slot.loss_sum.zero_()
+            args = self._args(slot.images, splan, slot.targets, slot.tweights, loss_scale, ws, slot.stash, True,
+                              slot.loss_sum, None, True)
+            with torch.cuda.device(self.device):
+                native.check(lib.pcg_guidance_fwd(C.byref(args), native.stream_ptr()), "pcg_guidance_fwd")
+            slot.launches_fwd = lib.pcg_last_launch_count()
+
+        if slot.fwd_graph is not None:
+            slot.fwd_graph.replay()
+        elif slot.calls_fwd >= 1:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                launch()
+            slot.fwd_graph = graph
+            graph.replay()
+        else:
+            launch()
+        slot.calls_fwd += 1
+        slot.owner = weakref.ref(token)
+        self.launches_fwd = slot.launches_fwd
+        return slot.loss_sum.clone()
+
+    def backward_graphed(self, slot: _GraphSlot, plan: CutPlan, loss_scale: float) -> torch.Tensor:
+        lib = native.lib()
+        splan = self._slot_plan(slot, plan, slot.images.shape[3])
+        ws = self._get_workspace(plan.n_local)
+
+        def launch():
+            slot.d_images.zero_()
+            args = self._args(slot.d_images, splan, slot.targets, slot.tweights, loss_scale, ws, slot.stash, True, None,
+                              None, True, d_images=slot.d_images)
+            args.images = None
+            with torch.cuda.device(self.device):
+                native.check(lib.pcg_guidance_bwd(C.byref(args), native.stream_ptr()), "pcg_guidance_bwd")
+            slot.launches_bwd = lib.pcg_last_launch_count()
+
+        if slot.bwd_graph is not None:
+            slot.bwd_graph.replay()
+        elif slot.calls_bwd >= 1 and not torch.cuda.is_current_stream_capturing():
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                launch()
+            slot.bwd_graph = graph
+            graph.replay()
+        else:
+            launch()
+        slot.calls_bwd += 1
+        slot.owner = None
+        self.launches_bwd = slot.launches_bwd
+        return slot.d_images.clone()
+
     def _check_images(self, images: torch.Tensor) -> None:
         if images.dim() != 4 or images.shape[1] != 3:
             raise ValueError(f"images must be [N,3,H,W], got {tuple(images.shape)}")
@@ -168,7 +305,13 @@ class GuidanceLossFn(torch.autograd.Function):
     def forward(ctx, images, engine: GuidanceEngine, plan: CutPlan, targets, tweights, multiplier, group):
         want_grad = ctx.needs_input_grad[0]
         scale = float(multiplier) / float(plan.n_total * targets.shape[0])
-        loss_sum, _, stash = engine.forward(images, plan, targets, tweights, scale, want_grad, False)
+        slot = engine._slot_for(images, plan, targets, tweights, scale) if want_grad else None
+        ctx.slot, ctx.token = slot, None
+        if slot is not None:
+            ctx.token = _Token()
+            loss_sum, stash = engine.forward_graphed(slot, images, plan, targets, tweights, scale, ctx.token), None
+        else:
+            loss_sum, _, stash = engine.forward(images, plan, targets, tweights, scale, want_grad, False)
         _all_reduce_sum(loss_sum, group)
         ctx.engine, ctx.plan, ctx.stash, ctx.group, ctx.scale = engine, plan, stash, group, scale
         ctx.targets, ctx.tweights, ctx.images_shape = targets, tweights, tuple(images.shape)
@@ -176,7 +319,12 @@ class GuidanceLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        d_images = ctx.engine.backward(ctx.images_shape, ctx.plan, ctx.stash, ctx.targets, ctx.tweights, ctx.scale)
+        if ctx.slot is not None:
+            if ctx.slot.owner is None or ctx.slot.owner() is not ctx.token:
+                raise RuntimeError("the activations of this forward were released (backward called twice?)")
+            d_images = ctx.engine.backward_graphed(ctx.slot, ctx.plan, ctx.scale)
+        else:
+            d_images = ctx.engine.backward(ctx.images_shape, ctx.plan, ctx.stash, ctx.targets, ctx.tweights, ctx.scale)
         ctx.stash = None
         _all_reduce_sum(d_images, ctx.group)
         return d_images * grad_out, None, None, None, None, None, None

@@ -235,3 +235,52 @@ def test_add_texts_through_the_module_api(cuda_device, tmp_path):
     x = torch.rand(1, 3, 64, 64, device=cuda_device).requires_grad_()
     loss(x).backward()
     assert torch.isfinite(x.grad).all()
+
+
+def test_cuda_graph_replay_matches_eager_launches(cuda_device):
+    """The loss path replays its ~100-400 launches from CUDA graphs after one eager and one capturing step; results
+    must equal the eager engine's on fresh cutouts every step, interleaved forwards must fall back to eager launches
+    instead of clobbering live activations, and an abandoned forward must not pin the slot."""
+    shape = SHAPES["ViT-B-32"]
+    sd = random_state_dict(shape, 4)
+    g = torch.Generator().manual_seed(12)
+    images = torch.rand(2, 3, 160, 192, generator=g).to(cuda_device)
+    targets = torch.nn.functional.normalize(torch.randn(2, shape.embed, generator=g)).to(cuda_device)
+    tw = torch.tensor([1.0, -0.5], device=cuda_device)
+    eng_g = GuidanceEngine(shape, sd, cuda_device, native.ACT_QUICKGELU)
+    eng_e = GuidanceEngine(shape, sd, cuda_device, native.ACT_QUICKGELU)
+    eng_e.use_graphs = False
+    assert eng_g.use_graphs
+    gen = torch.Generator().manual_seed(1)
+
+    def run(eng, rows):
+        img = images.clone().requires_grad_()
+        loss = GuidanceLossFn.apply(img, eng, eng.plan_cutouts(rows), targets, tw, 1.0, None)
+        loss.backward()
+        return float(loss.detach()), img.grad.clone()
+
+    for step in range(5):
+        rows = cutouts.sample_cutouts(gen, 2, 160, 192, 3, 1.0, 48, 160)
+        (lg, gg), (le, ge) = run(eng_g, rows), run(eng_e, rows)
+        assert abs(lg - le) <= 1e-6 * abs(le), (step, lg, le)
+        assert float((gg - ge).abs().max()) <= 1e-5 * float(ge.abs().max()), step  # fp32 atomics reorder only
+    slot = eng_g._slot
+    assert slot is not None and slot.fwd_graph is not None and slot.bwd_graph is not None and not slot.busy()
+
+    # two forwards alive at once: the second must not reuse the slot's activations
+    rows = cutouts.sample_cutouts(gen, 2, 160, 192, 3, 1.0, 48, 160)
+    a, b = images.clone().requires_grad_(), (images * 0.5).requires_grad_()
+    la = GuidanceLossFn.apply(a, eng_g, eng_g.plan_cutouts(rows), targets, tw, 1.0, None)
+    lb = GuidanceLossFn.apply(b, eng_g, eng_g.plan_cutouts(rows), targets, tw, 1.0, None)
+    (la + lb).backward()
+    _, ga = run(eng_e, rows)
+    assert float((a.grad - ga).abs().max()) <= 1e-5 * float(ga.abs().max())
+    assert torch.isfinite(b.grad).all() and not slot.busy()
+    # a forward whose loss is dropped releases the slot when its autograd node dies
+    dropped = GuidanceLossFn.apply(images.clone().requires_grad_(), eng_g, eng_g.plan_cutouts(rows), targets, tw, 1.0, None)
+    assert slot.busy()
+    del dropped
+    assert not slot.busy()
+    lg, gg = run(eng_g, rows)
+    le, ge = run(eng_e, rows)
+    assert abs(lg - le) <= 1e-6 * abs(le) and float((gg - ge).abs().max()) <= 1e-5 * float(ge.abs().max())
