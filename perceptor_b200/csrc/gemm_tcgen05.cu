@@ -457,7 +457,8 @@ int dispatch_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const 
 
 // Pick the N tile that minimises (waves x per-tile cost).  Per-tile MMA time is proportional to BN; narrow
 // tiles pay more shared-memory traffic per flop, hence the mild penalty.
-int choose_bn(int M, int N) {
+// Returns the tile width; *cost_out = modelled time in units of (one SM computing 128 rows x 1 column).
+int choose_bn(int M, int N, float* cost_out = nullptr) {
     const int sms = sm_count();
     const int cands[4] = {256, 192, 128, 64};
     const float penalty[4] = {1.00f, 1.03f, 1.10f, 1.45f};
@@ -474,7 +475,16 @@ int choose_bn(int M, int N) {
             best = bn;
         }
     }
+    if (cost_out != nullptr) *cost_out = best_cost;
     return best;
+}
+// The same model for CTA pairs (256 x 256 tiles over sms / 2 clusters): each SM of a pair computes 128 x 256 per
+// tile at ~0.92 of the single-CTA cost (measured in-step: 1210 vs 1113 TFLOP/s), but the wave count is quantised
+// on half as many slots -- with few tiles (ViT-B/32: 150 tiles of N = 768 on 74 pairs = 2.03 waves) a narrower
+// single-CTA tile wins.
+float pair_cost(int M, int N) {
+    const int waves = ceil_div(ceil_div(M, 256) * (N / 256), sm_count() / 2);
+    return static_cast<float>(waves) * 256.0f * 0.92f;
 }
 
 bool g_pair_enabled = []() {
@@ -497,9 +507,12 @@ int gemm_bf16_impl(int mode, int act, int M, int N, int K, const void* A, int ld
     PCG_CHECK_ARG((mode != PCG_GEMM_RESID_F32 && mode != PCG_GEMM_DACT) || aux, "pcg_gemm_bf16: mode needs aux");
     // CTA pairs (256 x 256 tiles) when the problem fills the 74 pairs with full-width tiles; force_bn 512 forces
     // them, any other force_bn the single-CTA kernel
+    float single_cost = 0.f;
+    const int single_bn = choose_bn(M, N, &single_cost);
     const bool pair = force_bn ? force_bn == 512
-                               : (g_pair_enabled && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= sm_count() / 2);
-    const int bn = pair ? 256 : (force_bn ? force_bn : choose_bn(M, N));
+                               : (g_pair_enabled && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= sm_count() / 2 &&
+                                  pair_cost(M, N) <= single_cost);
+    const int bn = pair ? 256 : (force_bn ? force_bn : single_bn);
     CUtensorMap ma, mb;
     int rc = get_tensor_map(&ma, A, M, K, lda, BM);
     if (rc) return rc;
