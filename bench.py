@@ -34,6 +34,11 @@ WORKLOADS = {
     "vit_b32_224_16cut_256px": ("ViT-B-32", 256, 16, 64, 1),
 }
 DEFAULT_WORKLOAD = "vit_l14_224_128cut_512px"
+# dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05_kernel launch, mean over the eight GEMM shapes of one
+# transformer layer (forward qkv / out / fc / proj, backward dproj / dfc / dout / dqkv) from the `ncu --set full`
+# captures summarised in profiles/r01d_gemm_{fwd,bwd}_ncu_full.csv.  It equals the operand + epilogue bytes of those
+# shapes (no re-reads): e.g. out-proj reads A 67 MB + residual 135 MB = 204 MB measured.
+NCU_GEMM_TRAFFIC_BYTES = {"vit_l14_224_128cut_512px": 363.7e6}
 METRIC = "CLIP-guidance cutouts/sec (loss + image grad), ViT-L/14, at 1/2/4/8 B200"
 
 
@@ -299,7 +304,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
                 "d2h_bytes_per_step": host_grad.numel() * 4 + 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": gemm_tflops, "peak": peak,
-                     "unit": "TFLOP/s", "frac": gemm_tflops / peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": gemm_tflops / peak,
+                     "traffic": NCU_GEMM_TRAFFIC_BYTES.get(args.workload),
+                     "traffic_unit": "bytes per launch (ncu dram read + write, mean over the layer's 8 GEMM shapes; "
+                                     "profiles/r01d_gemm_*_ncu_full.csv)",
                      "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches_timed": gemm["count"], "share_of_step": gemm["ms"] / prof_ms,
                      "timing": "CUDA event pair around every launch, second pass over the same K steps "
