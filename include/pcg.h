@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PCG_ABI_VERSION 1
+#define PCG_ABI_VERSION 2
 
 enum { PCG_ACT_QUICKGELU = 0, PCG_ACT_GELU = 1 };
 
@@ -119,7 +119,9 @@ int pcg_gemm_bf16(int mode, int act, int M, int N, int K, const void *A, int lda
  * replaces LayerNorm.forward (ruclip/model.py:11-17), eps = 1e-5. */
 int pcg_layernorm_fwd(const float *x, const float *gamma, const float *beta, void *y_bf16, int rows, int D,
                       void *stream);
-/* dx_io(f32) += LN'(x)^T dy ; also writes the bf16 copy of the updated dx (next dgrad GEMM operand). */
+/* dx += LN'(x)^T dy.  dx_io != NULL: the residual gradient is fp32 (dx_io, read and written) and dx_bf16 receives
+ * its bf16 copy (next dgrad GEMM operand).  dx_io == NULL: dx_bf16 IS the residual gradient, accumulated in place
+ * (10 instead of 16 bytes per element; what pcg_guidance_bwd uses). */
 int pcg_layernorm_bwd(const void *dy_bf16, const float *x, const float *gamma, float *dx_io, void *dx_bf16,
                       int rows, int D, void *stream);
 
@@ -127,9 +129,10 @@ int pcg_layernorm_bwd(const void *dy_bf16, const float *x, const float *gamma, f
  * patch_out f32 [n*g*g, D] -> v f32 [n*T, D] (pre-LN, stashed) and x0 f32 [n*T, D]. */
 int pcg_embed_fwd(const float *patch_out, const float *cls, const float *pos, const float *gamma,
                   const float *beta, float *v, float *x0, int n, int T, int D, void *stream);
-/* dx0 f32 [n*T,D] -> d_patch bf16 [n*g*g, D] (class-token rows dropped). */
-int pcg_embed_bwd(const float *dx0, const float *v, const float *gamma, void *d_patch_bf16, int n, int T, int D,
-                  void *stream);
+/* dx0 [n*T,D], given as f32 (dx0) or bf16 (dx0_bf16), exactly one non-NULL -> d_patch bf16 [n*g*g, D]
+ * (class-token rows dropped). */
+int pcg_embed_bwd(const float *dx0, const void *dx0_bf16, const float *v, const float *gamma, void *d_patch_bf16,
+                  int n, int T, int D, void *stream);
 
 /* ---- short-sequence multi-head attention, head dim 64, no mask ------------------------------------------
  * replaces nn.MultiheadAttention(need_weights=False) core (ruclip/model.py:43-49).
@@ -145,7 +148,8 @@ int pcg_attn_bwd(const void *qkv, const void *out, const void *d_out, const floa
  * enc_out (nullable) f32 [n,E] normalised (or raw if !normalize) encodings.
  * d_enc (nullable) f32 [n,E]: an upstream gradient w.r.t. the encodings; when given it replaces the loss
  *   gradient (this is autograd through encode_images for callers other than the CLIP loss).
- * dx (nullable) f32 [n*T, D]: CLS rows receive d(loss)/dx, all other rows are zeroed. dx_bf16 likewise.
+ * dx (nullable) f32 [n*T, D]: CLS rows receive d(loss)/dx, all other rows are zeroed. dx_bf16 (nullable) likewise;
+ *   either one (or both) requests the gradient.
  * workspace: pcg_head_workspace_bytes(n, D, E) bytes of device scratch (the batched projection's operands). */
 size_t pcg_head_workspace_bytes(int n, int D, int E);
 int pcg_head_loss(const float *x, const float *ln_g, const float *ln_b, const float *proj, const float *targets,

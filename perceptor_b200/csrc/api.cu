@@ -128,8 +128,7 @@ struct Work {
     float* patch_out;   // [P,D] f32  fwd: conv1 output;   bwd: d_patch bf16 [P,D] (aliases)
     uint16_t* y;        // [M,D]      LN output / dy
     uint16_t* a;        // [M,4D]     activation output / dH
-    float* dx;          // [M,D]
-    uint16_t* dxb;      // [M,D]
+    uint16_t* dxb;      // [M,D]      the residual-stream gradient (bf16, accumulated in place by the LN backward)
     uint16_t* dqkv;     // [M,3D]
     uint16_t* d_o;      // [M,D]
     float* delta;       // [n*heads*T]
@@ -146,7 +145,6 @@ Work carve_work(void* base, const pcg_vit_config& c, int n) {
     w.patch_out = b.take<float>(P * D);
     w.y = b.take<uint16_t>(M * D);
     w.a = b.take<uint16_t>(M * c.mlp);
-    w.dx = b.take<float>(M * D);
     w.dxb = b.take<uint16_t>(M * D);
     w.dqkv = b.take<uint16_t>(M * 3 * D);
     w.d_o = b.take<uint16_t>(M * D);
@@ -288,7 +286,7 @@ extern "C" int pcg_guidance_bwd(const pcg_guidance_args* a, void* stream) {
     // head: recompute the (tiny) forward of the head and emit d(loss)/dx at the class-token rows
     PCG_TRY(pcg_head_loss(stash_x(st, c.layers, true), w.ln_post_g, w.ln_post_b, w.proj, a->targets, a->tweights, n, T, D,
                           c.embed, a->targets ? a->n_targets : 0, a->d_enc ? 1.0f : a->loss_scale, a->normalize, nullptr,
-                          nullptr, a->d_enc, wk.dx, wk.dxb, wk.head_ws, stream));
+                          nullptr, a->d_enc, nullptr, wk.dxb, wk.head_ws, stream));
     for (int l = c.layers - 1; l >= 0; --l) {
         const pcg_layer_weights& lw = w.layers_host[l];
         const LayerStash ls = layer_stash(st, l, true);
@@ -297,17 +295,17 @@ extern "C" int pcg_guidance_bwd(const pcg_guidance_args* a, void* stream) {
                               c.mlp, stream));
         PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, c.mlp, wk.a, c.mlp, lw.w_fc_t, c.mlp, nullptr, nullptr, wk.y,
                               nullptr, D, stream));
-        PCG_TRY(pcg_layernorm_bwd(wk.y, ls.xb, lw.ln2_g, wk.dx, wk.dxb, M, D, stream));
+        PCG_TRY(pcg_layernorm_bwd(wk.y, ls.xb, lw.ln2_g, nullptr, wk.dxb, M, D, stream));
         // attention: dO = dx W_out ; dqkv = attn'(dO) ; dy = dqkv W_qkv ; dx += ln_1'(dy)
         PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, D, wk.dxb, D, lw.w_out_t, D, nullptr, nullptr, wk.d_o, nullptr,
                               D, stream));
         PCG_TRY(pcg_attn_bwd(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream));
         PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, 3 * D, wk.dqkv, 3 * D, lw.w_qkv_t, 3 * D, nullptr, nullptr,
                               wk.y, nullptr, D, stream));
-        PCG_TRY(pcg_layernorm_bwd(wk.y, stash_x(st, l, true), lw.ln1_g, wk.dx, wk.dxb, M, D, stream));
+        PCG_TRY(pcg_layernorm_bwd(wk.y, stash_x(st, l, true), lw.ln1_g, nullptr, wk.dxb, M, D, stream));
     }
     uint16_t* d_patch = reinterpret_cast<uint16_t*>(wk.patch_out);  // bf16 [P,D] fits in the f32 [P,D] buffer
-    PCG_TRY(pcg_embed_bwd(wk.dx, st.v, w.ln_pre_g, d_patch, n, T, D, stream));
+    PCG_TRY(pcg_embed_bwd(nullptr, wk.dxb, st.v, w.ln_pre_g, d_patch, n, T, D, stream));
     PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, P, c.kpad, D, d_patch, D, w.conv1_t, D, nullptr, nullptr, wk.patches,
                           nullptr, c.kpad, stream));
     PCG_TRY(pcg_sampler_bwd(wk.patches, nullptr, a->B, a->H, a->W, a->cuts, n, a->tabs, c.image_size, c.patch, c.kpad,

@@ -110,8 +110,11 @@ __device__ __forceinline__ float4 bf16x4_to_float4(uint2 u) {
     return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
 }
 
-// dx_io += LN_bwd(dy) ; dx_bf16 = bf16(dx_io).  All three input streams are requested before the first reduction.
-template <int NV>
+// dx += LN_bwd(dy).  kF32: the residual gradient lives in fp32 (dx_io, 16 B/element) with a bf16 copy for the next
+// dgrad GEMM; !kF32: the bf16 tensor IS the residual gradient, accumulated in place (10 B/element) -- the production
+// backward: 48 bf16 roundings cost ~1e-4 of gradient cosine (tolerance 1e-3) and 37 % of this kernel's traffic.
+// All input streams are requested before the first reduction.
+template <int NV, bool kF32>
 __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     float* __restrict__ dx_io, bf16* __restrict__ dx_bf16,
@@ -123,19 +126,20 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const bf16* 
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
     float4* dxr = reinterpret_cast<float4*>(dx_io + static_cast<size_t>(row) * D);
+    uint2* dbr = reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(row) * D);
     float4 v[NV], g[NV], acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         v[i] = xr[i * 32 + lane];
         g[i] = bf16x4_to_float4(dyr[i * 32 + lane]);
-        acc[i] = dxr[i * 32 + lane];
+        if constexpr (kF32) acc[i] = dxr[i * 32 + lane];
+        else acc[i] = bf16x4_to_float4(dbr[i * 32 + lane]);
     }
     ln_bwd_row<NV>(v, g, gamma, lane);
-    uint2* dbr = reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(row) * D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const float4 d = make_float4(acc[i].x + g[i].x, acc[i].y + g[i].y, acc[i].z + g[i].z, acc[i].w + g[i].w);
-        dxr[i * 32 + lane] = d;
+        if constexpr (kF32) dxr[i * 32 + lane] = d;
         dbr[i * 32 + lane] = pack4(d.x, d.y, d.z, d.w);
     }
 }
@@ -177,8 +181,8 @@ __global__ void __launch_bounds__(kRowThreads) embed_fwd_kernel(const float* __r
 }
 
 // d_patch[n*g*g + t-1] = bf16( ln_pre'(v)^T dx0[n*T + t] ), t >= 1
-template <int NV>
-__global__ void __launch_bounds__(kRowThreads) embed_bwd_kernel(const float* __restrict__ dx0, const float* __restrict__ v,
+template <int NV, bool kF32>
+__global__ void __launch_bounds__(kRowThreads) embed_bwd_kernel(const void* __restrict__ dx0, const float* __restrict__ v,
                                                                 const float* __restrict__ gamma, bf16* __restrict__ d_patch,
                                                                 int n, int T) {
     constexpr int D = NV * 128;
@@ -188,12 +192,12 @@ __global__ void __launch_bounds__(kRowThreads) embed_bwd_kernel(const float* __r
     const int nn = prow / (T - 1), t = prow % (T - 1) + 1;
     const size_t row = static_cast<size_t>(nn) * T + t;
     const float4* vr = reinterpret_cast<const float4*>(v + row * D);
-    const float4* dr = reinterpret_cast<const float4*>(dx0 + row * D);
     float4 xv[NV], g[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         xv[i] = vr[i * 32 + lane];
-        g[i] = dr[i * 32 + lane];
+        if constexpr (kF32) g[i] = reinterpret_cast<const float4*>(static_cast<const float*>(dx0) + row * D)[i * 32 + lane];
+        else g[i] = bf16x4_to_float4(reinterpret_cast<const uint2*>(static_cast<const bf16*>(dx0) + row * D)[i * 32 + lane]);
     }
     ln_bwd_row<NV>(xv, g, gamma, lane);
     uint2* out = reinterpret_cast<uint2*>(d_patch + static_cast<size_t>(prow) * D);
@@ -211,6 +215,19 @@ __global__ void __launch_bounds__(kRowThreads) embed_bwd_kernel(const float* __r
         case 8: KERNEL<8><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
         case 10: KERNEL<10><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                           \
         case 12: KERNEL<12><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        default: return ::pcg::set_error(-1, "width %d is not one of 128*{1,2,4,6,8,10,12}", (D));           \
+    }
+
+// the same for kernels templated on <NV, bool>
+#define PCG_DISPATCH_NV2(D, KERNEL, FLAG, GRID, STREAM, ...)                                                 \
+    switch ((D) >> 7) {                                                                                      \
+        case 1: KERNEL<1, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
+        case 2: KERNEL<2, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
+        case 4: KERNEL<4, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
+        case 6: KERNEL<6, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
+        case 8: KERNEL<8, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
+        case 10: KERNEL<10, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                     \
+        case 12: KERNEL<12, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                     \
         default: return ::pcg::set_error(-1, "width %d is not one of 128*{1,2,4,6,8,10,12}", (D));           \
     }
 
@@ -383,12 +400,12 @@ head_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, 
     }
     const float c1 = block_sum(s1, red) / D;
     const float c2 = block_sum(s2, red) / D;
-    float* dxr = dx + static_cast<size_t>(n) * T * D;
+    float* dxr = dx ? dx + static_cast<size_t>(n) * T * D : nullptr;
     bf16* dbr = dx_bf16 ? dx_bf16 + static_cast<size_t>(n) * T * D : nullptr;
     for (int d = tid; d < D; d += kHeadThreads) {
         const float xh = (xr[d] - mean) * rstd;
         const float gval = rstd * (gr[d] * ln_g[d] - c1 - xh * c2);
-        dxr[d] = gval;
+        if (dxr) dxr[d] = gval;
         if (dbr) dbr[d] = __float2bfloat16(gval);
     }
 }
@@ -416,11 +433,16 @@ extern "C" int pcg_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int pcg_layernorm_bwd(const void* dy_bf16, const float* x, const float* gamma, float* dx_io, void* dx_bf16,
                                  int rows, int D, void* stream) {
-    PCG_CHECK_ARG(dy_bf16 && x && gamma && dx_io && dx_bf16 && rows > 0, "pcg_layernorm_bwd: bad arguments");
+    PCG_CHECK_ARG(dy_bf16 && x && gamma && dx_bf16 && rows > 0, "pcg_layernorm_bwd: bad arguments");
     if (int rc = check_d("pcg_layernorm_bwd", D)) return rc;
-    ProfileScope prof(PCG_PROF_LAYERNORM, 16.0 * rows * D, static_cast<cudaStream_t>(stream));
-    PCG_DISPATCH_NV(D, layernorm_bwd_kernel, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream),
-                    static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows);
+    ProfileScope prof(PCG_PROF_LAYERNORM, (dx_io ? 16.0 : 10.0) * rows * D, static_cast<cudaStream_t>(stream));
+    if (dx_io != nullptr) {
+        PCG_DISPATCH_NV2(D, layernorm_bwd_kernel, true, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream),
+                         static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows);
+    } else {
+        PCG_DISPATCH_NV2(D, layernorm_bwd_kernel, false, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream),
+                         static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows);
+    }
     PCG_LAUNCH_CHECK("layernorm_bwd_kernel");
     return 0;
 }
@@ -436,13 +458,19 @@ extern "C" int pcg_embed_fwd(const float* patch_out, const float* cls, const flo
     return 0;
 }
 
-extern "C" int pcg_embed_bwd(const float* dx0, const float* v, const float* gamma, void* d_patch_bf16, int n, int T,
-                             int D, void* stream) {
-    PCG_CHECK_ARG(dx0 && v && gamma && d_patch_bf16 && n > 0 && T > 1, "pcg_embed_bwd: bad arguments");
+extern "C" int pcg_embed_bwd(const float* dx0, const void* dx0_bf16, const float* v, const float* gamma,
+                             void* d_patch_bf16, int n, int T, int D, void* stream) {
+    PCG_CHECK_ARG((dx0 != nullptr) != (dx0_bf16 != nullptr), "pcg_embed_bwd: pass exactly one of dx0 / dx0_bf16");
+    PCG_CHECK_ARG(v && gamma && d_patch_bf16 && n > 0 && T > 1, "pcg_embed_bwd: bad arguments");
     if (int rc = check_d("pcg_embed_bwd", D)) return rc;
-    ProfileScope prof(PCG_PROF_EMBED, 10.0 * n * T * D, static_cast<cudaStream_t>(stream));
-    PCG_DISPATCH_NV(D, embed_bwd_kernel, ceil_div(n * (T - 1), kRowsPerBlock), static_cast<cudaStream_t>(stream), dx0, v,
-                    gamma, static_cast<bf16*>(d_patch_bf16), n, T);
+    ProfileScope prof(PCG_PROF_EMBED, (dx0 ? 10.0 : 8.0) * n * T * D, static_cast<cudaStream_t>(stream));
+    if (dx0 != nullptr) {
+        PCG_DISPATCH_NV2(D, embed_bwd_kernel, true, ceil_div(n * (T - 1), kRowsPerBlock), static_cast<cudaStream_t>(stream),
+                         static_cast<const void*>(dx0), v, gamma, static_cast<bf16*>(d_patch_bf16), n, T);
+    } else {
+        PCG_DISPATCH_NV2(D, embed_bwd_kernel, false, ceil_div(n * (T - 1), kRowsPerBlock), static_cast<cudaStream_t>(stream),
+                         dx0_bf16, v, gamma, static_cast<bf16*>(d_patch_bf16), n, T);
+    }
     PCG_LAUNCH_CHECK("embed_bwd_kernel");
     return 0;
 }
@@ -459,19 +487,18 @@ extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_
     PCG_CHECK_ARG(x && ln_g && ln_b && proj && workspace && n > 0 && T > 0 && D > 0 && E > 0,
                   "pcg_head_loss: bad arguments");
     PCG_CHECK_ARG(M == 0 || (targets && tweights), "pcg_head_loss: targets/tweights missing for M=%d", M);
-    PCG_CHECK_ARG(dx == nullptr || M > 0 || d_enc, "pcg_head_loss: a gradient needs targets or d_enc");
+    const bool want_dx = dx != nullptr || dx_bf16 != nullptr;
+    PCG_CHECK_ARG(!want_dx || M > 0 || d_enc, "pcg_head_loss: a gradient needs targets or d_enc");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t smem = static_cast<size_t>(2 * E) * sizeof(float);
     PCG_CHECK_ARG(smem <= 48 * 1024, "pcg_head_loss: E=%d exceeds the shared-memory budget", E);
-    ProfileScope prof(PCG_PROF_HEAD, (dx ? 6.0 : 0.0) * n * T * D + (dx ? 4.0 : 2.0) * n * D * E, s);
+    ProfileScope prof(PCG_PROF_HEAD, ((dx ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0)) * n * T * D + (want_dx ? 4.0 : 2.0) * n * D * E, s);
     float* y = workspace;                             // [n, D] ln_post output
     float* dy = y + static_cast<size_t>(n) * D;       // [n, D]
     float* z = dy + static_cast<size_t>(n) * D;       // [n, E]
     float* dz = z + static_cast<size_t>(n) * E;       // [n, E]
-    if (dx != nullptr) {
-        PCG_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(n) * T * D * sizeof(float), s));
-        if (dx_bf16 != nullptr) PCG_CUDA(cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(n) * T * D * 2, s));
-    }
+    if (dx != nullptr) PCG_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(n) * T * D * sizeof(float), s));
+    if (dx_bf16 != nullptr) PCG_CUDA(cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(n) * T * D * 2, s));
     head_ln_kernel<<<n, kHeadThreads, 0, s>>>(x, ln_g, ln_b, T, D, y);
     PCG_LAUNCH_CHECK("head_ln_kernel");
     head_gemm_kernel<false><<<dim3(ceil_div(E, kHgCols), ceil_div(n, kHgRows)), kHeadThreads, 0, s>>>(y, proj, z, n, E, D);
@@ -479,9 +506,9 @@ extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_
     const bool has_loss = targets != nullptr && M > 0;
     if (!has_loss && d_enc == nullptr && enc_out == nullptr) return 0;
     head_dist_kernel<<<n, kHeadThreads, smem, s>>>(z, has_loss ? targets : nullptr, tweights, E, has_loss ? M : 0, scale,
-                                                   normalize, loss_sum, enc_out, d_enc, dx ? dz : nullptr);
+                                                   normalize, loss_sum, enc_out, d_enc, want_dx ? dz : nullptr);
     PCG_LAUNCH_CHECK("head_dist_kernel");
-    if (dx == nullptr) return 0;
+    if (!want_dx) return 0;
     head_gemm_kernel<true><<<dim3(ceil_div(D, kHgCols), ceil_div(n, kHgRows)), kHeadThreads, 0, s>>>(dz, proj, dy, n, D, E);
     PCG_LAUNCH_CHECK("head_gemm_kernel");
     head_ln_bwd_kernel<<<n, kHeadThreads, 0, s>>>(x, ln_g, dy, T, D, dx, static_cast<bf16*>(dx_bf16));

@@ -16,7 +16,7 @@ LIB_PATH = PKG_DIR / "libpcg.so"
 ACT_QUICKGELU, ACT_GELU = 0, 1
 GEMM_BF16, GEMM_BIAS_ACT, GEMM_RESID_F32, GEMM_DACT, GEMM_F32 = 0, 1, 2, 3, 4
 CUT_STRIDE = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -85,7 +85,7 @@ SIGNATURES = {
     "pcg_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "pcg_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "pcg_embed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "pcg_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pcg_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_head_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -40,8 +40,10 @@ def layernorm_fwd(x, gamma, beta):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, dx_io):
-    dxb = torch.empty(x.shape, dtype=bf16, device=x.device)
+def layernorm_bwd(dy, x, gamma, dx_io=None, dx_bf16=None):
+    """dx += LN'(x)^T dy.  With `dx_io` (f32, updated in place) the bf16 copy is returned; with `dx_bf16` alone the
+    bf16 tensor is the accumulator (updated in place and returned)."""
+    dxb = dx_bf16 if dx_bf16 is not None else torch.empty(x.shape, dtype=bf16, device=x.device)
     native.check(native.lib().pcg_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(dx_io), _p(dxb), x.shape[0], x.shape[1],
                                                 native.stream_ptr()), "pcg_layernorm_bwd")
     return dxb
@@ -59,8 +61,9 @@ def embed_fwd(patch_out, cls, pos, gamma, beta, n, tokens):
 def embed_bwd(dx0, v, gamma, n, tokens):
     d = v.shape[1]
     out = torch.empty((n * (tokens - 1), d), dtype=bf16, device=v.device)
-    native.check(native.lib().pcg_embed_bwd(_p(dx0), _p(v), _p(gamma), _p(out), n, tokens, d, native.stream_ptr()),
-                 "pcg_embed_bwd")
+    f32 = dx0.dtype == torch.float32
+    native.check(native.lib().pcg_embed_bwd(_p(dx0) if f32 else None, None if f32 else _p(dx0), _p(v), _p(gamma), _p(out),
+                                            n, tokens, d, native.stream_ptr()), "pcg_embed_bwd")
     return out
 
 

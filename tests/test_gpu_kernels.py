@@ -124,6 +124,11 @@ def test_layernorm(cuda_device, rows, d):
     dxb = ops.layernorm_bwd(dy, x, gamma, dx)
     check_close(dx, dx0 + xr.grad, 1e-5, "layernorm bwd (f32 accumulate)")
     check_close(dxb, dx0 + xr.grad, 4e-3, "layernorm bwd (bf16 copy)")
+    # production mode: the bf16 tensor is the residual gradient, accumulated in place
+    acc = dx0.to(bf16)
+    out = ops.layernorm_bwd(dy, x, gamma, dx_bf16=acc)
+    assert out.data_ptr() == acc.data_ptr()
+    check_close(acc, dx0.to(bf16).float() + xr.grad, 4e-3, "layernorm bwd (bf16 accumulate in place)")
 
 
 # ------------------------------------------------------------------------------------------------ embed
@@ -146,6 +151,11 @@ def test_embed(cuda_device, n, grid, d):
     x_ref.backward(dx0.reshape(n, t, d))
     got = ops.embed_bwd(dx0, v, gamma, n, t)
     check_close(got, pr.grad, 4e-3, "embed bwd")
+    pr.grad = None
+    x_ref2 = torch.nn.functional.layer_norm(torch.cat([cls.expand(n, 1, d), pr.reshape(n, grid * grid, d)], dim=1) + pos,
+                                            (d,), gamma, beta, 1e-5)
+    x_ref2.backward(dx0.to(bf16).float().reshape(n, t, d))
+    check_close(ops.embed_bwd(dx0.to(bf16), v, gamma, n, t), pr.grad, 4e-3, "embed bwd (bf16 upstream gradient)")
 
 
 # ------------------------------------------------------------------------------------------------ attention
