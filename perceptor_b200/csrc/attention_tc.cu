@@ -709,6 +709,7 @@ struct BwdParams {
     bf16* d_qkv;
     long long* trace;
     int wave;  // CTAs resident at once (one per SM): the L2 prefetch distance
+    int stagger_cycles;  // first wave: SM s starts (s % 8) * stagger_cycles late, see the kernel
 };
 
 // 16 columns of one block for this thread's key row: P^T = exp2(S^T log2e - lse2), dS^T = P^T (dP^T - delta) as
@@ -829,6 +830,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const size_t vbase = (static_cast<size_t>(n) * p.heads + h) * p.T;
     const size_t cta_id = static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x;
     if (warp == 0) PCG_TRACE(0);
+
+    // One CTA per SM and equal work per CTA: left alone, all 148 CTAs load their 192 KB of operands at the same
+    // moment, compute at the same moment and store at the same moment, so the operand loads run at 1/148 of the L2
+    // bandwidth each while the L2 idles the rest of the time.  Delaying the first wave by a per-SM offset spreads the
+    // phases out; the offsets persist because every SM runs its CTAs back to back.
+    if (p.stagger_cycles > 0 && cta_id < static_cast<size_t>(p.wave)) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const long long wait = static_cast<long long>((smid >> 1) & 7) * p.stagger_cycles;
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) {
+        }
+    }
 
     // delta = rowsum(dO * O) per query needs O, which no MMA reads: the elementwise warps fetch their rows of O and
     // dO straight from global / L2 (eight lanes share a 128-byte row, four rows per step) at kernel entry, so the
@@ -1135,6 +1149,10 @@ bool use_tc(int T) { return T >= 66 && T <= 257; }
 bool use_flash_fwd(int T) { return T > 257; }
 
 long long* g_trace = nullptr;
+int g_bwd_stagger = []() {
+    const char* e = getenv("PCG_ATTN_BWD_STAGGER");
+    return e != nullptr ? atoi(e) : 2500;  // measured: 279 us (0) -> 274 us (2500) per ViT-L/14 layer, 6000 is worse
+}();
 int g_fwd_stagger = []() {
     const char* e = getenv("PCG_ATTN_STAGGER");
     return e != nullptr ? atoi(e) : 5000;
@@ -1225,7 +1243,7 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
     }
     const int nv = T - 1;
     BwdParams p{T,   heads, nv, (nv + 127) / 128, static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
-                static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace, sm_count()};  // delta: in-kernel
+                static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace, sm_count(), g_bwd_stagger};  // delta: in-kernel
     attn_bwd_tc_kernel<<<dim3(heads, n), kBwdThreads, kBwdSmemBytes, s>>>(map, map_do, p);
     PCG_LAUNCH_CHECK("attn_bwd_tc_kernel");
     return 0;
