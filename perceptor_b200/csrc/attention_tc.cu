@@ -342,7 +342,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
         if (lane == 0) {
             const int nblk = (nk + 127) >> 7;
             // pull the operands of the CTA that takes this slot next (stagger_ctas = CTAs resident at once) into L2;
-            // the tiles of one head share K and V, so only the first tile's CTA prefetches those
+            // the tiles of one head share K and V, so only the first tile's CTA prefetches those.  (Issued before this
+            // CTA's own loads have landed: forward CTAs are short, later costs more lead time than it saves.)
             const size_t next = cta_id + p.stagger_ctas;
             if (next < static_cast<size_t>(gridDim.x) * gridDim.y * gridDim.z) {
                 const int t2 = static_cast<int>(next % gridDim.x);
@@ -360,7 +361,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
             mma_tile_x_rows(tmem, sm_q, sm_k, nk);  // S = Q K^T
             umma_commit(&bars[2]);
             mbar_wait(&bars[1], 0);  // V landed
-            PCG_TRACE(3);
             // O = P V with A = P from TMEM (8 columns of bf16 pairs per 16 keys), keys >= 128 first
             const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
             const int ksteps = nk >> 4;
@@ -845,21 +845,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     }
 
     // delta = rowsum(dO * O) per query needs O, which no MMA reads: the elementwise warps fetch their rows of O and
-    // dO straight from global / L2 (eight lanes share a 128-byte row, four rows per step) at kernel entry, so the
-    // latency hides behind the setup and the operand loads.
-    uint4 xo[8], xd[8];
-    if (warp < 8) {
+    // dO straight from global / L2 (eight lanes share a 128-byte row, four rows per step).  Like the operand tiles,
+    // the rows are requested in the order they are needed: query block 0 at kernel entry (the latency hides behind
+    // the setup), query block 1 once those have been reduced (it is needed after the first block's arithmetic).
+    uint4 xo[4], xd[4];
+    auto load_o_rows = [&](int half) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int row = warp * 32 + it * 4 + (lane >> 3);
+        for (int it = 0; it < 4; ++it) {
+            const int row = half * 128 + warp * 16 + it * 4 + (lane >> 3);
             const size_t off = (static_cast<size_t>(n) * p.T + min(row, nv)) * D + h * kHd + (lane & 7) * 8;
             xo[it] = *reinterpret_cast<const uint4*>(p.out + off);
             xd[it] = *reinterpret_cast<const uint4*>(p.d_out + off);
         }
-        const size_t next = cta_id + p.wave;  // the next head's O rows (its dO rows come with the TMA prefetch)
-        if (next < static_cast<size_t>(gridDim.x) * gridDim.y && threadIdx.x <= nv)
-            prefetch_l2(p.out + (static_cast<size_t>(next / gridDim.x) * p.T + threadIdx.x) * D + (next % gridDim.x) * kHd);
-    }
+    };
+    if (warp < 8) load_o_rows(0);
 
     if (warp == 8) {
         if (lane == 0) {
@@ -876,15 +875,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             tma_load_3d(&map_qkv, &bars[0], sm_q, h * kHd, 0, n, kEvictFirst);
             tma_load_3d(&map_qkv, &bars[0], sm_v, 2 * D + h * kHd, 0, n, kEvictFirst);
             tma_load_3d(&map_do, &bars[0], sm_do, h * kHd, 0, n, kEvictFirst);
-            if (nt > 1) {
-                mbar_arrive_expect_tx(&bars[1], 4 * kBlkBytes);
-                tma_load_3d(&map_qkv, &bars[1], sm_q + kBlkBytes, h * kHd, 128, n, kEvictFirst);
-                tma_load_3d(&map_do, &bars[1], sm_do + kBlkBytes, h * kHd, 128, n, kEvictFirst);
-                tma_load_3d(&map_qkv, &bars[1], sm_k + kBlkBytes, D + h * kHd, 128, n, kEvictFirst);
-                tma_load_3d(&map_qkv, &bars[1], sm_v + kBlkBytes, 2 * D + h * kHd, 128, n, kEvictFirst);
-            } else {
-                mbar_arrive(&bars[1]);
-            }
+            // the second tile's operands are requested once the first tile's have landed (below): asking for all
+            // 128 KB at once only delays the 64 KB the first block is waiting for
+            if (nt == 1) mbar_arrive(&bars[1]);
         }
         __syncwarp();
         tmem_alloc(tmem_slot, 512);
@@ -916,22 +909,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             // block b = (key tile j, query block i), j-major; widths of the query blocks
             auto width = [&](int i) { return min(128, ((nv - 128 * i) + 15) & ~15); };
             // pull the operands of the head that runs on this SM next (one wave ahead) into L2
-            const size_t next = cta_id + p.wave;
-            if (next < static_cast<size_t>(gridDim.x) * gridDim.y) {
-                const int h2 = static_cast<int>(next % gridDim.x), n2 = static_cast<int>(next / gridDim.x);
-                for (int i = 0; i < nt; ++i) {
-                    tma_prefetch_3d(&map_qkv, D + h2 * kHd, i * 128, n2);
-                    tma_prefetch_3d(&map_qkv, h2 * kHd, i * 128, n2);
-                    tma_prefetch_3d(&map_qkv, 2 * D + h2 * kHd, i * 128, n2);
-                    tma_prefetch_3d(&map_do, h2 * kHd, i * 128, n2);
+            auto prefetch_next = [&]() {
+                const size_t next = cta_id + p.wave;
+                if (next < static_cast<size_t>(gridDim.x) * gridDim.y) {
+                    const int h2 = static_cast<int>(next % gridDim.x), n2 = static_cast<int>(next / gridDim.x);
+                    for (int i = 0; i < nt; ++i) {
+                        tma_prefetch_3d(&map_qkv, D + h2 * kHd, i * 128, n2);
+                        tma_prefetch_3d(&map_qkv, h2 * kHd, i * 128, n2);
+                        tma_prefetch_3d(&map_qkv, 2 * D + h2 * kHd, i * 128, n2);
+                        tma_prefetch_3d(&map_do, h2 * kHd, i * 128, n2);
+                    }
                 }
-            }
+            };
             mbar_wait(&bars[0], 0);
             PCG_TRACE(1);
             tc_fence_after();
             mma_tile_x_rows(tmem + kColST, sm_k, sm_q, width(0));    // S^T  = K_0 Q_0^T
             mma_tile_x_rows(tmem + kColDPT, sm_v, sm_do, width(0));  // dP^T = V_0 dO_0^T
             umma_commit(&bars[2]);
+            if (nt > 1) {
+                mbar_arrive_expect_tx(&bars[1], 4 * kBlkBytes);
+                tma_load_3d(&map_qkv, &bars[1], sm_q + kBlkBytes, h * kHd, 128, n, kEvictFirst);
+                tma_load_3d(&map_do, &bars[1], sm_do + kBlkBytes, h * kHd, 128, n, kEvictFirst);
+                tma_load_3d(&map_qkv, &bars[1], sm_k + kBlkBytes, D + h * kHd, 128, n, kEvictFirst);
+                tma_load_3d(&map_qkv, &bars[1], sm_v + kBlkBytes, 2 * D + h * kHd, 128, n, kEvictFirst);
+            }
+            prefetch_next();  // (behind this head's own loads: 276 -> 269 us per layer)
             mbar_wait(&bars[1], 0);
             tc_fence_after();
             for (int b = 0; b < n_blocks; ++b) {
@@ -1002,17 +1005,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
         uint8_t* stage = sm + kBwdOffStage + warp * 2048;
         bf16* gd = p.d_qkv + static_cast<size_t>(n) * p.T * 3 * D + h * kHd + phase * 32;
-        // delta = rowsum(dO * O): reduce the chunks loaded at kernel entry over the 8 lanes of each row
+        // delta = rowsum(dO * O): reduce the loaded chunks over the 8 lanes of each row
+        auto reduce_delta = [&](int half) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int row = warp * 32 + it * 4 + (lane >> 3);
-            float d = chunk_dot(xo[it], xd[it]);
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            if ((lane & 7) == 0) delta[row] = (row < nv) ? d : 0.f;
+            for (int it = 0; it < 4; ++it) {
+                const int row = half * 128 + warp * 16 + it * 4 + (lane >> 3);
+                float d = chunk_dot(xo[it], xd[it]);
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if ((lane & 7) == 0) delta[row] = (row < nv) ? d : 0.f;
+            }
+        };
+        reduce_delta(0);
+        load_o_rows(1);
+        {
+            const size_t next = cta_id + p.wave;  // the next head's O rows (its dO rows come with the TMA prefetch)
+            if (next < static_cast<size_t>(gridDim.x) * gridDim.y && threadIdx.x <= nv)
+                prefetch_l2(p.out + (static_cast<size_t>(next / gridDim.x) * p.T + threadIdx.x) * D + (next % gridDim.x) * kHd);
         }
-        named_bar_sync(1, kBwdThreads - 32);
+        named_bar_sync(2, 256);  // delta of query block 0 is complete (the elementwise warps only)
         if (warp == 0) PCG_TRACE(20);
         int b = 0;
         for (int j = 0; j < nt; ++j) {
@@ -1060,6 +1072,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[4]);
                 if (warp == 0) PCG_TRACE(5 + 2 * b);
+                if (b == 0) {
+                    reduce_delta(1);
+                    named_bar_sync(1, kBwdThreads - 32);  // all of delta[] is complete (with the edge warps)
+                }
             }
             // key tile j finished: dV_j and dK_j (+ the edge query's contribution) -> global
             if (j == 0) mbar_wait(&bars[6], 0);
