@@ -138,6 +138,9 @@ int pcg_embed_bwd(const float *dx0, const void *dx0_bf16, const float *v, const 
  * replaces nn.MultiheadAttention(need_weights=False) core (ruclip/model.py:43-49).
  * qkv bf16 [n*T, 3D] (q pre-scaled), out bf16 [n*T, D], lse f32 [n, heads, T] (natural log). */
 int pcg_attn_fwd(const void *qkv, void *out, float *lse, int n, int T, int heads, void *stream);
+/* delta_ws: pcg_attn_bwd_workspace_bytes(n, T, heads) bytes of scratch (rowsum(dO*O) per query; for T > 257 also the
+ * fp32 dQ sums that the key-tile CTAs of the tcgen05 backward reduce into). */
+size_t pcg_attn_bwd_workspace_bytes(int n, int T, int heads);
 int pcg_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse, float *delta_ws,
                  void *d_qkv, int n, int T, int heads, void *stream);
 

@@ -131,7 +131,7 @@ struct Work {
     uint16_t* dxb;      // [M,D]      the residual-stream gradient (bf16, accumulated in place by the LN backward)
     uint16_t* dqkv;     // [M,3D]
     uint16_t* d_o;      // [M,D]
-    float* delta;       // [n*heads*T]
+    float* delta;       // pcg_attn_bwd_workspace_bytes: [n*heads*T] (+ f32 dQ sums [M,D] for long sequences)
     float* head_ws;     // pcg_head_workspace_bytes
     void* nostash;      // forward-only stash region
     size_t total;
@@ -148,7 +148,7 @@ Work carve_work(void* base, const pcg_vit_config& c, int n) {
     w.dxb = b.take<uint16_t>(M * D);
     w.dqkv = b.take<uint16_t>(M * 3 * D);
     w.d_o = b.take<uint16_t>(M * D);
-    w.delta = b.take<float>(static_cast<size_t>(n) * c.heads * c.tokens);
+    w.delta = b.take<float>(pcg_attn_bwd_workspace_bytes(n, c.tokens, c.heads) / sizeof(float));
     w.head_ws = b.take<float>(pcg_head_workspace_bytes(n, c.width, c.embed) / sizeof(float));
     w.nostash = base ? static_cast<uint8_t*>(base) + b.off : nullptr;
     b.off += carve_stash(nullptr, c, n, 1).total;

@@ -495,9 +495,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
 //   l = l alpha + rowsum P_c,  O = O alpha (tcgen05.ld / st on the 64 accumulator columns, alpha = exp2(m - m'))
 //   ->  O += P_c V_c (A = P_c from TMEM).
 // The MMAs of one chunk and the softmax of the same chunk are serial inside a CTA; the second CTA of the SM fills
-// the gaps.  The edge key (token T - 1) enters as the initial maximum and in the epilogue exactly as above; the
-// edge QUERY row is left to the mma.sync kernel (one row per head: it would need every K / V chunk a second time).
-constexpr int kFlashOffBar = kFwdOffX + 512;  // float k_x[64], v_x[64]; then 8 mbarriers + tmem slot
+// the gaps.  There is no edge token here: with five or more tiles the class token simply rides in the last,
+// partly filled tile (577 = 4 x 128 + 65), p.nv = T.
+constexpr int kFlashOffBar = kFwdOffX;  // 8 mbarriers + tmem slot
 constexpr int kFlashSmemBytes = kFlashOffBar + 128 + 1024;
 constexpr uint32_t kFlashColO = 128;
 enum { kFbK = 0, kFbV = 2, kFbS = 4, kFbP = 5, kFbO = 6, kFbX = 7 };
@@ -510,8 +510,6 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdPara
     uint8_t* sm_k = sm;             // two stages of [128 keys x 64]
     uint8_t* sm_v = sm + kFwdOffV;  // two stages
     uint8_t* sm_q = sm + kFwdOffQ;
-    float* kx = reinterpret_cast<float*>(sm + kFwdOffX);
-    float* vx = kx + 64;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kFlashOffBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
@@ -522,7 +520,6 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdPara
     const int nc = (nv + 127) >> 7;
     const size_t cta_id = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 
-    uint32_t xk = 0, xv = 0;
     if (warp == 4) {
         if (lane == 0) {
             mbar_init(&bars[kFbK], 1);
@@ -558,10 +555,6 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdPara
         __syncwarp();
         tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
-    } else if (warp == 5) {
-        const bf16* xrow_g = p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd + 2 * lane;
-        xk = *reinterpret_cast<const uint32_t*>(xrow_g + D);
-        xv = *reinterpret_cast<const uint32_t*>(xrow_g + 2 * D);
     }
     tc_fence_before();
     __syncthreads();
@@ -602,10 +595,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdPara
     } else if (warp < 4) {
         const int r = warp * 32 + lane;
         const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-        mbar_wait(&bars[kFbX], 0);
-        mbar_wait(&bars[kFbK], 0);
-        const float sx = row_dot(sm_q, r, kx);  // score against the edge key
-        float mx = sx, sum = 0.f;
+        float mx = -INFINITY, sum = 0.f;
         for (int c = 0; c < nc; ++c) {
             const int nvl = min(128, nv - c * 128);  // valid keys of this chunk
             const int cend = (nvl + 31) & ~31;
@@ -636,8 +626,6 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdPara
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kFbP]);
         }
-        const float px = exp2f((sx - mx) * kLog2e);
-        sum += px;
         if (q0 + r < nv) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + q0 + r] = mx + logf(sum);
         const float inv = 1.0f / sum;
         mbar_wait(&bars[kFbO], (nc - 1) & 1);
@@ -648,16 +636,10 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdPara
         tmem_wait_ld();
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-            const float4 xa = *reinterpret_cast<const float4*>(vx + g * 8);
-            const float4 xb = *reinterpret_cast<const float4*>(vx + g * 8 + 4);
-            const uint4 o = make_uint4(pack_bf16(fmaf(px, xa.x, __uint_as_float(v[8 * g])) * inv,
-                                                 fmaf(px, xa.y, __uint_as_float(v[8 * g + 1])) * inv),
-                                       pack_bf16(fmaf(px, xa.z, __uint_as_float(v[8 * g + 2])) * inv,
-                                                 fmaf(px, xa.w, __uint_as_float(v[8 * g + 3])) * inv),
-                                       pack_bf16(fmaf(px, xb.x, __uint_as_float(v[8 * g + 4])) * inv,
-                                                 fmaf(px, xb.y, __uint_as_float(v[8 * g + 5])) * inv),
-                                       pack_bf16(fmaf(px, xb.z, __uint_as_float(v[8 * g + 6])) * inv,
-                                                 fmaf(px, xb.w, __uint_as_float(v[8 * g + 7])) * inv));
+            const uint4 o = make_uint4(pack_bf16(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
+                                       pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
+                                       pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
+                                       pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
             *reinterpret_cast<uint4*>(sm_q + row_chunk(r, g)) = o;
         }
         __syncwarp();
@@ -669,11 +651,6 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdPara
                 *reinterpret_cast<uint4*>(gout + static_cast<size_t>(q0 + row) * D + ch * 8) =
                     *reinterpret_cast<const uint4*>(sm_q + row_chunk(row, ch));
         }
-    } else {
-        kx[2 * lane] = bf_lo(xk), kx[2 * lane + 1] = bf_hi(xk);
-        vx[2 * lane] = bf_lo(xv), vx[2 * lane + 1] = bf_hi(xv);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[kFbX]);
     }
     tc_fence_before();
     __syncthreads();
@@ -752,7 +729,8 @@ __device__ __forceinline__ void bwd_store16(const Cols16& o, uint8_t* pt_blk, ui
     }
 }
 
-// 32 accumulator columns of this thread's row + coef * xrow[.] -> bf16 -> the warp's staging rows -> global
+// 32 accumulator columns of this thread's row (+ coef * xrow[.] when kEdge) -> bf16 -> the warp's staging rows -> global
+template <bool kEdge = true>
 __device__ __forceinline__ void bwd_epilogue(uint32_t taddr, float coef, const float* xrow, uint8_t* stage, int lane,
                                              bf16* gbase, size_t ld, int row0, int row_end) {
     uint32_t v[32];
@@ -761,8 +739,11 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t taddr, float coef, const f
     const int sw = (lane >> 1) & 3;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        const float4 xa = *reinterpret_cast<const float4*>(xrow + g * 8);
-        const float4 xb = *reinterpret_cast<const float4*>(xrow + g * 8 + 4);
+        float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+        if constexpr (kEdge) {
+            xa = *reinterpret_cast<const float4*>(xrow + g * 8);
+            xb = *reinterpret_cast<const float4*>(xrow + g * 8 + 4);
+        }
         const uint4 o = make_uint4(pack_bf16(fmaf(coef, xa.x, __uint_as_float(v[8 * g])),
                                              fmaf(coef, xa.y, __uint_as_float(v[8 * g + 1]))),
                                    pack_bf16(fmaf(coef, xa.z, __uint_as_float(v[8 * g + 2])),
@@ -1102,6 +1083,234 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// backward, long sequences (T > 257: ViT-L/14 @336)
+// ---------------------------------------------------------------------------------------------------------
+// The fused backward above keeps one dQ accumulator per query block in tensor memory, which stops at two blocks
+// (512 columns).  Here one CTA owns ONE key tile j of a (cutout, head) and walks every query block i:
+//   S^T = K_j Q_i^T, dP^T = V_j dO_i^T -> P^T, dS^T (shared memory) -> dV_j += P^T dO_i, dK_j += dS^T Q_i (TMEM,
+//   complete when the walk ends) and the PARTIAL dQ_i = dS K_j of this key tile, which is drained from TMEM after
+//   every block and reduced across the key-tile CTAs with fp32 vector reductions (red.global.add.v4.f32) into a
+//   workspace; a small kernel converts the sums to bf16 afterwards.  Q_i / dO_i stream through a two-stage ring.
+// All T tokens are tiled (no edge token: 577 = 4 x 128 + 65); delta = rowsum(dO O) comes from attn_delta_kernel.
+// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ partial 64 = 448 of 512 columns, one CTA per SM.
+constexpr int kLongThreads = 288;  // warps 0-7 elementwise, warp 8 TMA + MMA
+constexpr int kLongMaxT = 1152;
+constexpr int kLongOffK = 0;
+constexpr int kLongOffV = 1 * kBlkBytes;
+constexpr int kLongOffQ = 2 * kBlkBytes;    // two stages
+constexpr int kLongOffDO = 4 * kBlkBytes;   // two stages
+constexpr int kLongOffPT = 6 * kBlkBytes;   // P^T [128 keys x 128 queries], two 64-column blocks
+constexpr int kLongOffDST = 8 * kBlkBytes;  // dS^T
+constexpr int kLongOffStage = 10 * kBlkBytes;
+constexpr int kLongOffVec = 11 * kBlkBytes;  // float lse2[kLongMaxT], delta[kLongMaxT]
+constexpr int kLongOffBar = kLongOffVec + 2 * kLongMaxT * 4;
+constexpr int kLongSmemBytes = kLongOffBar + 128 + 1024;
+constexpr uint32_t kColDQp = 384;
+enum { kLbLd = 0, kLbS = 2, kLbA = 3, kLbB = 4, kLbG = 5, kLbD = 6 };
+
+struct LongParams {
+    int T, heads;
+    const float* lse;
+    const float* delta;
+    float* dq_ws;  // f32 [n*T, D], zeroed by the caller
+    bf16* d_qkv;
+};
+
+__global__ void __launch_bounds__(kLongThreads, 1)
+attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                     const LongParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sm_k = sm + kLongOffK;
+    uint8_t* sm_v = sm + kLongOffV;
+    uint8_t* sm_q = sm + kLongOffQ;
+    uint8_t* sm_do = sm + kLongOffDO;
+    uint8_t* sm_pt = sm + kLongOffPT;
+    uint8_t* sm_dst = sm + kLongOffDST;
+    float* lse2 = reinterpret_cast<float*>(sm + kLongOffVec);
+    float* delta = lse2 + kLongMaxT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kLongOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+    const int T = p.T, D = p.heads * kHd;
+    const int nq = (T + 127) >> 7;
+    const size_t vbase = (static_cast<size_t>(n) * p.heads + h) * T;
+    auto width = [&](int i) { return min(128, ((T - 128 * i) + 15) & ~15); };
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(&bars[kLbLd], 1);
+            mbar_init(&bars[kLbLd + 1], 1);
+            mbar_init(&bars[kLbS], 1);
+            mbar_init(&bars[kLbA], 8);
+            mbar_init(&bars[kLbB], 8);
+            mbar_init(&bars[kLbG], 1);
+            mbar_init(&bars[kLbD], 8);
+            fence_barrier_init();
+            mbar_arrive_expect_tx(&bars[kLbLd], 4 * kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[kLbLd], sm_k, D + h * kHd, j * 128, n, kEvictNormal);
+            tma_load_3d(&map_qkv, &bars[kLbLd], sm_q, h * kHd, 0, n, kEvictNormal);
+            tma_load_3d(&map_qkv, &bars[kLbLd], sm_v, 2 * D + h * kHd, j * 128, n, kEvictNormal);
+            tma_load_3d(&map_do, &bars[kLbLd], sm_do, h * kHd, 0, n, kEvictNormal);
+            if (nq > 1) {
+                mbar_arrive_expect_tx(&bars[kLbLd + 1], 2 * kBlkBytes);
+                tma_load_3d(&map_qkv, &bars[kLbLd + 1], sm_q + kBlkBytes, h * kHd, 128, n, kEvictNormal);
+                tma_load_3d(&map_do, &bars[kLbLd + 1], sm_do + kBlkBytes, h * kHd, 128, n, kEvictNormal);
+            }
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    } else {
+        // per-query softmax statistics of the whole sequence: lse * log2(e) (+inf past the end: p = 0), delta
+        for (int t = threadIdx.x; t < nq * 128; t += 256) {
+            lse2[t] = (t < T) ? p.lse[vbase + t] * kLog2e : INFINITY;
+            delta[t] = (t < T) ? p.delta[vbase + t] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < nq; ++i) {
+                const int st = i & 1;
+                const int ksteps = width(i) >> 4, k_lo = min(ksteps, 4);
+                const uint8_t* q_i = sm_q + st * kBlkBytes;
+                const uint8_t* do_i = sm_do + st * kBlkBytes;
+                mbar_wait(&bars[kLbLd + st], (i >> 1) & 1);
+                tc_fence_after();
+                // queued behind the gradient MMAs of block i - 1, which read the P^T / dS^T buffers the elementwise
+                // warps refill once these two have retired
+                mma_tile_x_rows(tmem + kColST, sm_k, q_i, width(i));    // S^T  = K_j Q_i^T
+                mma_tile_x_rows(tmem + kColDPT, sm_v, do_i, width(i));  // dP^T = V_j dO_i^T
+                umma_commit(&bars[kLbS]);
+                if (i >= 1 && i + 1 < nq) {
+                    // the other stage held block i - 1: free once its gradient MMAs have retired
+                    mbar_wait(&bars[kLbG], (i - 1) & 1);
+                    const int s2 = st ^ 1;
+                    mbar_arrive_expect_tx(&bars[kLbLd + s2], 2 * kBlkBytes);
+                    tma_load_3d(&map_qkv, &bars[kLbLd + s2], sm_q + s2 * kBlkBytes, h * kHd, (i + 1) * 128, n, kEvictNormal);
+                    tma_load_3d(&map_do, &bars[kLbLd + s2], sm_do + s2 * kBlkBytes, h * kHd, (i + 1) * 128, n, kEvictNormal);
+                }
+                mbar_wait(&bars[kLbA], i & 1);
+                tc_fence_after();
+                mma_blocks_x_cols(tmem + kColDV, sm_pt, do_i, k_lo, i != 0);
+                mma_blocks_x_cols(tmem + kColDK, sm_dst, q_i, k_lo, i != 0);
+                mbar_wait(&bars[kLbB], i & 1);
+                tc_fence_after();
+                if (ksteps > 4) {
+                    mma_blocks_x_cols(tmem + kColDV, sm_pt + kBlkBytes, do_i + 4 * 2048, ksteps - 4, true);
+                    mma_blocks_x_cols(tmem + kColDK, sm_dst + kBlkBytes, q_i + 4 * 2048, ksteps - 4, true);
+                }
+                if (i >= 1) {
+                    mbar_wait(&bars[kLbD], (i - 1) & 1);  // the previous partial dQ has been drained
+                    tc_fence_after();
+                }
+                mma_rows_t_x_cols(tmem + kColDQp, sm_dst, sm_k, 8, false);  // partial dQ_i = dS K_j
+                umma_commit(&bars[kLbG]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3, phase = warp >> 2;
+        const int r = quarter * 32 + lane;  // key row of the tile (S^T, dV, dK) / query row of the block (dQ) == TMEM lane
+        const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint8_t* stage = sm + kLongOffStage + warp * 2048;
+        const bool row_ok = (j * 128 + r) < T;
+        for (int i = 0; i < nq; ++i) {
+            const int wd = width(i);
+            const float* l2 = lse2 + i * 128;
+            const float* dl = delta + i * 128;
+            mbar_wait(&bars[kLbS], i & 1);
+            tc_fence_after();
+            const int c0 = phase * 32, c1 = 64 + phase * 32;
+            uint32_t sa[16], da[16], sb[16], db[16];
+            Cols16 o;
+            if (c0 < wd) tmem_ld<16>(trow + kColST + c0, sa), tmem_ld<16>(trow + kColDPT + c0, da);
+            tmem_wait_ld();
+            if (c0 + 16 < wd) tmem_ld<16>(trow + kColST + c0 + 16, sb), tmem_ld<16>(trow + kColDPT + c0 + 16, db);
+            if (c0 < wd) {
+                o = bwd_cols16(sa, da, l2 + c0, dl + c0, row_ok);
+                bwd_store16(o, sm_pt, sm_dst, r, c0 >> 3);
+            }
+            tmem_wait_ld();
+            if (c1 < wd) tmem_ld<16>(trow + kColST + c1, sa), tmem_ld<16>(trow + kColDPT + c1, da);
+            if (c0 + 16 < wd) {
+                o = bwd_cols16(sb, db, l2 + c0 + 16, dl + c0 + 16, row_ok);
+                bwd_store16(o, sm_pt, sm_dst, r, (c0 + 16) >> 3);
+            }
+            tmem_wait_ld();
+            if (c1 + 16 < wd) tmem_ld<16>(trow + kColST + c1 + 16, sb), tmem_ld<16>(trow + kColDPT + c1 + 16, db);
+            if (c1 < wd) o = bwd_cols16(sa, da, l2 + c1, dl + c1, row_ok);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kLbA]);
+            if (c1 < wd) bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 - 64) >> 3);
+            tmem_wait_ld();
+            if (c1 + 16 < wd) {
+                o = bwd_cols16(sb, db, l2 + c1 + 16, dl + c1 + 16, row_ok);
+                bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 + 16 - 64) >> 3);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kLbB]);
+            // this key tile's share of dQ_i: TMEM -> fp32 vector reductions into the workspace (the S^T / dP^T MMAs
+            // of the next block are already queued behind it, so the tensor pipe does not wait for the drain)
+            mbar_wait(&bars[kLbG], i & 1);
+            tc_fence_after();
+            {
+                uint32_t v[32];
+                tmem_ld<32>(trow + kColDQp + phase * 32, v);
+                tmem_wait_ld();
+                const int q = i * 128 + r;
+                if (q < T) {
+                    float* dst = p.dq_ws + (static_cast<size_t>(n) * T + q) * D + h * kHd + phase * 32;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+                                     "f"(__uint_as_float(v[4 * g])), "f"(__uint_as_float(v[4 * g + 1])),
+                                     "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3]))
+                                     : "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kLbD]);
+        }
+        // dV_j, dK_j are complete (the last wait on kLbG covered every MMA)
+        bf16* gd = p.d_qkv + static_cast<size_t>(n) * T * 3 * D + h * kHd + phase * 32;
+        const int row0 = j * 128 + quarter * 32;
+        bwd_epilogue<false>(trow + kColDV + phase * 32, 0.f, nullptr, stage, lane, gd + 2 * D, static_cast<size_t>(3) * D,
+                            row0, T);
+        bwd_epilogue<false>(trow + kColDK + phase * 32, 0.f, nullptr, stage, lane, gd + D, static_cast<size_t>(3) * D, row0,
+                            T);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// dQ sums (f32 [rows, D]) -> the q third of d_qkv (bf16 [rows, 3D]); 8 elements per thread
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ dq, bf16* __restrict__ d_qkv,
+                                                              size_t rows, int D) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int per_row = D >> 3;
+    if (idx >= rows * per_row) return;
+    const size_t row = idx / per_row;
+    const int c = static_cast<int>(idx - row * per_row) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(dq + row * D + c);
+    const float4 b = *reinterpret_cast<const float4*>(dq + row * D + c + 4);
+    *reinterpret_cast<uint4*>(d_qkv + row * 3 * D + c) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------
 using EncodeFn = PFN_cuTensorMapEncodeTiled_v12000;
@@ -1163,6 +1372,8 @@ int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols) {
 // T - 1 <= 256: everything in tensor memory at once (forward) / one fused backward; beyond that the streaming forward.
 bool use_tc(int T) { return T >= 66 && T <= 257; }
 bool use_flash_fwd(int T) { return T > 257; }
+bool use_long_bwd(int T) { return T > 257 && T <= kLongMaxT; }
+size_t bwd_delta_floats(int n, int T, int heads) { return align_up(static_cast<size_t>(n) * heads * T, 64); }
 
 long long* g_trace = nullptr;
 int g_bwd_stagger = []() {
@@ -1210,12 +1421,11 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
             PCG_CUDA(cudaFuncSetAttribute(attn_fwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlashSmemBytes));
             flash_configured = true;
         }
-        const int nvf = T - 1;
-        FwdParams pf{T, heads, nvf, (nvf + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
+        FwdParams pf{T, heads, T, (T + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
                      nullptr, 2 * sm_count(), g_fwd_stagger};
-        attn_fwd_flash_kernel<<<dim3((nvf + 127) / 128, heads, n), kFwdThreads, kFlashSmemBytes, s>>>(map, pf);
+        attn_fwd_flash_kernel<<<dim3((T + 127) / 128, heads, n), kFwdThreads, kFlashSmemBytes, s>>>(map, pf);
         PCG_LAUNCH_CHECK("attn_fwd_flash_kernel");
-        return attn_fwd_legacy(qkv, out, lse, n, T, heads, nvf, s);  // the edge query row
+        return 0;
     }
     static bool configured = false;
     if (!configured) {
@@ -1237,6 +1447,13 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     return 0;
 }
 
+extern "C" size_t pcg_attn_bwd_workspace_bytes(int n, int T, int heads) {
+    if (n <= 0 || T <= 0 || heads <= 0) return 0;
+    size_t floats = bwd_delta_floats(n, T, heads);
+    if (use_long_bwd(T)) floats += static_cast<size_t>(n) * T * heads * kHd;  // fp32 dQ sums of the key-tile CTAs
+    return floats * sizeof(float);
+}
+
 extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, float* delta_ws,
                             void* d_qkv, int n, int T, int heads, void* stream) {
     PCG_CHECK_ARG(qkv && out && d_out && lse && delta_ws && d_qkv, "pcg_attn_bwd: null pointer");
@@ -1244,11 +1461,33 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
     PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "pcg_attn_bwd: n and heads must be <= 65535");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ProfileScope prof(PCG_PROF_ATTN_BWD, 8.0 * T * T * kHd * heads * n, s);
+    const int D = heads * kHd;
+    if (!g_force_legacy && use_long_bwd(T)) {
+        CUtensorMap lmap, lmap_do;
+        if (int rc = make_map3(&lmap, qkv, n, T, 3 * D)) return rc;
+        if (int rc = make_map3(&lmap_do, d_out, n, T, D)) return rc;
+        static bool long_configured = false;
+        if (!long_configured) {
+            PCG_CUDA(cudaFuncSetAttribute(attn_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongSmemBytes));
+            long_configured = true;
+        }
+        if (int rc = attn_delta(out, d_out, delta_ws, n, T, heads, s)) return rc;
+        float* dq_ws = delta_ws + bwd_delta_floats(n, T, heads);
+        const size_t rows = static_cast<size_t>(n) * T;
+        PCG_CUDA(cudaMemsetAsync(dq_ws, 0, rows * D * sizeof(float), s));
+        LongParams lp{T, heads, lse, delta_ws, dq_ws, static_cast<bf16*>(d_qkv)};
+        attn_bwd_long_kernel<<<dim3((T + 127) / 128, heads, n), kLongThreads, kLongSmemBytes, s>>>(lmap, lmap_do, lp);
+        PCG_LAUNCH_CHECK("attn_bwd_long_kernel");
+        const size_t items = rows * (D / 8);
+        attn_dq_convert_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, s>>>(dq_ws, static_cast<bf16*>(d_qkv),
+                                                                                         rows, D);
+        PCG_LAUNCH_CHECK("attn_dq_convert_kernel");
+        return 0;
+    }
     if (g_force_legacy || !use_tc(T)) {
         if (int rc = attn_delta(out, d_out, delta_ws, n, T, heads, s)) return rc;
         return attn_bwd_legacy(qkv, d_out, lse, delta_ws, d_qkv, n, T, heads, 0, s);
     }
-    const int D = heads * kHd;
     CUtensorMap map, map_do;
     if (int rc = make_map3(&map, qkv, n, T, 3 * D)) return rc;
     if (int rc = make_map3(&map_do, d_out, n, T, D)) return rc;

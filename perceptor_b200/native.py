@@ -87,6 +87,7 @@ SIGNATURES = {
     "pcg_embed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pcg_attn_bwd_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "pcg_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_head_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcg_head_workspace_bytes": (C.c_size_t, [_i, _i, _i]),

@@ -78,7 +78,8 @@ def attn_fwd(qkv, n, tokens, heads):
 
 def attn_bwd(qkv, out, d_out, lse, n, tokens, heads):
     d_qkv = torch.empty_like(qkv)
-    delta = torch.empty((n, heads, tokens), dtype=torch.float32, device=qkv.device)
+    delta = torch.empty(native.lib().pcg_attn_bwd_workspace_bytes(n, tokens, heads) // 4, dtype=torch.float32,
+                        device=qkv.device)
     native.check(native.lib().pcg_attn_bwd(_p(qkv), _p(out), _p(d_out), _p(lse), _p(delta), _p(d_qkv), n, tokens, heads,
                                            native.stream_ptr()), "pcg_attn_bwd")
     return d_qkv
