@@ -1100,13 +1100,13 @@ constexpr int kLongOffV = 1 * kBlkBytes;
 constexpr int kLongOffQ = 2 * kBlkBytes;    // two stages
 constexpr int kLongOffDO = 4 * kBlkBytes;   // two stages
 constexpr int kLongOffPT = 6 * kBlkBytes;   // P^T [128 keys x 128 queries], two 64-column blocks
-constexpr int kLongOffDST = 8 * kBlkBytes;  // dS^T
-constexpr int kLongOffStage = 10 * kBlkBytes;
-constexpr int kLongOffVec = 11 * kBlkBytes;  // float lse2[kLongMaxT], delta[kLongMaxT]
+constexpr int kLongOffDST = 8 * kBlkBytes;  // dS^T, two buffers (block parity): dQ_i = dS K_j reads one while the next block fills the other
+constexpr int kLongOffStage = 12 * kBlkBytes;
+constexpr int kLongOffVec = 13 * kBlkBytes;  // float lse2[kLongMaxT], delta[kLongMaxT]
 constexpr int kLongOffBar = kLongOffVec + 2 * kLongMaxT * 4;
 constexpr int kLongSmemBytes = kLongOffBar + 128 + 1024;
 constexpr uint32_t kColDQp = 384;
-enum { kLbLd = 0, kLbS = 2, kLbA = 3, kLbB = 4, kLbG = 5, kLbD = 6 };
+enum { kLbLd = 0, kLbS = 2, kLbA = 3, kLbB = 4, kLbG = 5, kLbD = 6, kLbF = 7 };
 
 struct LongParams {
     int T, heads;
@@ -1149,6 +1149,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
             mbar_init(&bars[kLbB], 8);
             mbar_init(&bars[kLbG], 1);
             mbar_init(&bars[kLbD], 8);
+            mbar_init(&bars[kLbF], 1);
             fence_barrier_init();
             mbar_arrive_expect_tx(&bars[kLbLd], 4 * kBlkBytes);
             tma_load_3d(&map_qkv, &bars[kLbLd], sm_k, D + h * kHd, j * 128, n, kEvictNormal);
@@ -1178,21 +1179,29 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 
     if (warp == 8) {
         if (lane == 0) {
+            // MMA order per block i: [S^T_i, dP^T_i] (first block only; later ones are issued early, see below) ->
+            // dV / dK halves as P^T_i / dS^T_i arrive -> S^T_{i+1}, dP^T_{i+1} -> partial dQ_i.  The next block's scores
+            // are queued AHEAD of dQ_i so that the elementwise warps start on them while dQ_i (which reads the other
+            // dS^T buffer) is still running; the tensor pipe retires in order, so everything that read P^T or the
+            // dS^T buffer of block i - 1 is done before S^T_{i+1} signals.
+            auto issue_scores = [&](int i) {
+                const int st = i & 1;
+                mbar_wait(&bars[kLbLd + st], (i >> 1) & 1);
+                tc_fence_after();
+                mma_tile_x_rows(tmem + kColST, sm_k, sm_q + st * kBlkBytes, width(i));    // S^T  = K_j Q_i^T
+                mma_tile_x_rows(tmem + kColDPT, sm_v, sm_do + st * kBlkBytes, width(i));  // dP^T = V_j dO_i^T
+                umma_commit(&bars[kLbS]);
+            };
+            issue_scores(0);
             for (int i = 0; i < nq; ++i) {
                 const int st = i & 1;
                 const int ksteps = width(i) >> 4, k_lo = min(ksteps, 4);
                 const uint8_t* q_i = sm_q + st * kBlkBytes;
                 const uint8_t* do_i = sm_do + st * kBlkBytes;
-                mbar_wait(&bars[kLbLd + st], (i >> 1) & 1);
-                tc_fence_after();
-                // queued behind the gradient MMAs of block i - 1, which read the P^T / dS^T buffers the elementwise
-                // warps refill once these two have retired
-                mma_tile_x_rows(tmem + kColST, sm_k, q_i, width(i));    // S^T  = K_j Q_i^T
-                mma_tile_x_rows(tmem + kColDPT, sm_v, do_i, width(i));  // dP^T = V_j dO_i^T
-                umma_commit(&bars[kLbS]);
+                const uint8_t* dst_i = sm_dst + st * 2 * kBlkBytes;
                 if (i >= 1 && i + 1 < nq) {
-                    // the other stage held block i - 1: free once its gradient MMAs have retired
-                    mbar_wait(&bars[kLbG], (i - 1) & 1);
+                    // the other stage held Q / dO of block i - 1: free once dV and dK of that block have retired
+                    mbar_wait(&bars[kLbF], (i - 1) & 1);
                     const int s2 = st ^ 1;
                     mbar_arrive_expect_tx(&bars[kLbLd + s2], 2 * kBlkBytes);
                     tma_load_3d(&map_qkv, &bars[kLbLd + s2], sm_q + s2 * kBlkBytes, h * kHd, (i + 1) * 128, n, kEvictNormal);
@@ -1201,18 +1210,20 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
                 mbar_wait(&bars[kLbA], i & 1);
                 tc_fence_after();
                 mma_blocks_x_cols(tmem + kColDV, sm_pt, do_i, k_lo, i != 0);
-                mma_blocks_x_cols(tmem + kColDK, sm_dst, q_i, k_lo, i != 0);
+                mma_blocks_x_cols(tmem + kColDK, dst_i, q_i, k_lo, i != 0);
                 mbar_wait(&bars[kLbB], i & 1);
                 tc_fence_after();
                 if (ksteps > 4) {
                     mma_blocks_x_cols(tmem + kColDV, sm_pt + kBlkBytes, do_i + 4 * 2048, ksteps - 4, true);
-                    mma_blocks_x_cols(tmem + kColDK, sm_dst + kBlkBytes, q_i + 4 * 2048, ksteps - 4, true);
+                    mma_blocks_x_cols(tmem + kColDK, dst_i + kBlkBytes, q_i + 4 * 2048, ksteps - 4, true);
                 }
+                umma_commit(&bars[kLbF]);
+                if (i + 1 < nq) issue_scores(i + 1);
                 if (i >= 1) {
                     mbar_wait(&bars[kLbD], (i - 1) & 1);  // the previous partial dQ has been drained
                     tc_fence_after();
                 }
-                mma_rows_t_x_cols(tmem + kColDQp, sm_dst, sm_k, 8, false);  // partial dQ_i = dS K_j
+                mma_rows_t_x_cols(tmem + kColDQp, dst_i, sm_k, 8, false);  // partial dQ_i = dS K_j
                 umma_commit(&bars[kLbG]);
             }
         }
@@ -1222,10 +1233,32 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
         uint8_t* stage = sm + kLongOffStage + warp * 2048;
         const bool row_ok = (j * 128 + r) < T;
+        // this key tile's share of dQ_i: TMEM -> fp32 vector reductions into the workspace
+        auto drain_dq = [&](int i) {
+            mbar_wait(&bars[kLbG], i & 1);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld<32>(trow + kColDQp + phase * 32, v);
+            tmem_wait_ld();
+            const int q = i * 128 + r;
+            if (q < T) {
+                float* dst = p.dq_ws + (static_cast<size_t>(n) * T + q) * D + h * kHd + phase * 32;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+                                 "f"(__uint_as_float(v[4 * g])), "f"(__uint_as_float(v[4 * g + 1])),
+                                 "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3]))
+                                 : "memory");
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kLbD]);
+        };
         for (int i = 0; i < nq; ++i) {
             const int wd = width(i);
             const float* l2 = lse2 + i * 128;
             const float* dl = delta + i * 128;
+            uint8_t* dst_i = sm_dst + (i & 1) * 2 * kBlkBytes;
             mbar_wait(&bars[kLbS], i & 1);
             tc_fence_after();
             const int c0 = phase * 32, c1 = 64 + phase * 32;
@@ -1236,13 +1269,13 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
             if (c0 + 16 < wd) tmem_ld<16>(trow + kColST + c0 + 16, sb), tmem_ld<16>(trow + kColDPT + c0 + 16, db);
             if (c0 < wd) {
                 o = bwd_cols16(sa, da, l2 + c0, dl + c0, row_ok);
-                bwd_store16(o, sm_pt, sm_dst, r, c0 >> 3);
+                bwd_store16(o, sm_pt, dst_i, r, c0 >> 3);
             }
             tmem_wait_ld();
             if (c1 < wd) tmem_ld<16>(trow + kColST + c1, sa), tmem_ld<16>(trow + kColDPT + c1, da);
             if (c0 + 16 < wd) {
                 o = bwd_cols16(sb, db, l2 + c0 + 16, dl + c0 + 16, row_ok);
-                bwd_store16(o, sm_pt, sm_dst, r, (c0 + 16) >> 3);
+                bwd_store16(o, sm_pt, dst_i, r, (c0 + 16) >> 3);
             }
             tmem_wait_ld();
             if (c1 + 16 < wd) tmem_ld<16>(trow + kColST + c1 + 16, sb), tmem_ld<16>(trow + kColDPT + c1 + 16, db);
@@ -1250,39 +1283,19 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kLbA]);
-            if (c1 < wd) bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 - 64) >> 3);
+            if (c1 < wd) bwd_store16(o, sm_pt + kBlkBytes, dst_i + kBlkBytes, r, (c1 - 64) >> 3);
             tmem_wait_ld();
             if (c1 + 16 < wd) {
                 o = bwd_cols16(sb, db, l2 + c1 + 16, dl + c1 + 16, row_ok);
-                bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 + 16 - 64) >> 3);
+                bwd_store16(o, sm_pt + kBlkBytes, dst_i + kBlkBytes, r, (c1 + 16 - 64) >> 3);
             }
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kLbB]);
-            // this key tile's share of dQ_i: TMEM -> fp32 vector reductions into the workspace (the S^T / dP^T MMAs
-            // of the next block are already queued behind it, so the tensor pipe does not wait for the drain)
-            mbar_wait(&bars[kLbG], i & 1);
-            tc_fence_after();
-            {
-                uint32_t v[32];
-                tmem_ld<32>(trow + kColDQp + phase * 32, v);
-                tmem_wait_ld();
-                const int q = i * 128 + r;
-                if (q < T) {
-                    float* dst = p.dq_ws + (static_cast<size_t>(n) * T + q) * D + h * kHd + phase * 32;
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
-                                     "f"(__uint_as_float(v[4 * g])), "f"(__uint_as_float(v[4 * g + 1])),
-                                     "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3]))
-                                     : "memory");
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[kLbD]);
+            if (i >= 1) drain_dq(i - 1);  // behind this block's arithmetic: dQ_{i-1} retired while it ran
         }
+        drain_dq(nq - 1);
         // dV_j, dK_j are complete (the last wait on kLbG covered every MMA)
         bf16* gd = p.d_qkv + static_cast<size_t>(n) * T * 3 * D + h * kHd + phase * 32;
         const int row0 = j * 128 + quarter * 32;
