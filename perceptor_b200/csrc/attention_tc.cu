@@ -1,5 +1,8 @@
-// tcgen05 short-sequence attention for 66 <= T <= 257 (ViT-B/16: 197, ViT-L/14: 257), head dim 64: forward and a
-// single fused backward (dQ, dK, dV in one pass, S and dP computed once).
+// tcgen05 attention for ViT sequences, head dim 64.  Two kernel pairs:
+//   * 66 <= T <= 257 (ViT-B/16: 197, ViT-L/14: 257): forward with all of S in tensor memory and a single fused
+//     backward (dQ, dK, dV in one pass, S and dP computed once), both built on the decomposition below;
+//   * 257 < T <= 1152 (ViT-L/14 @336: 577): a streaming forward (online softmax over 128-key chunks) and a backward
+//     with one CTA per key tile whose partial dQ is reduced with fp32 vector reductions; see the sections further down.
 //
 // "256 + 1" decomposition.  A ViT sequence is a power-of-two patch grid plus the class token, so T - 1 tokens
 // tile exactly into 128-row tensor-core tiles and the one left-over token (the "edge" token x = T - 1, both as a
@@ -1448,14 +1451,7 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     const int nv = T - 1;
     FwdParams p{T, heads, nv, (nv + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
                 g_trace, 2 * sm_count(), g_fwd_stagger};
-    static const int smem_pad = []() {  // experiment: PCG_ATTN_FWD_ONE=1 forces one CTA per SM
-        const char* e = getenv("PCG_ATTN_FWD_ONE");
-        return (e != nullptr && e[0] == '1') ? 40 * 1024 : 0;
-    }();
-    if (smem_pad)
-        PCG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kFwdSmemBytes + smem_pad));
-    attn_fwd_tc_kernel<<<dim3((nv + 127) / 128, heads, n), kFwdThreads, kFwdSmemBytes + smem_pad, s>>>(map, p);
+    attn_fwd_tc_kernel<<<dim3((nv + 127) / 128, heads, n), kFwdThreads, kFwdSmemBytes, s>>>(map, p);
     PCG_LAUNCH_CHECK("attn_fwd_tc_kernel");
     return 0;
 }
