@@ -732,6 +732,12 @@ __device__ __forceinline__ void bwd_store16(const Cols16& o, uint8_t* pt_blk, ui
     }
 }
 
+// dS^T only (the packed kernels keep P^T in tensor memory)
+__device__ __forceinline__ void bwd_store_ds(const Cols16& o, uint8_t* dst_blk, int r, int chunk0) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) *reinterpret_cast<uint4*>(dst_blk + row_chunk(r, chunk0 + g)) = o.ds[g];
+}
+
 // 32 accumulator columns of this thread's row (+ coef * xrow[.] when kEdge) -> bf16 -> the warp's staging rows -> global
 template <bool kEdge = true>
 __device__ __forceinline__ void bwd_epilogue(uint32_t taddr, float coef, const float* xrow, uint8_t* stage, int lane,
@@ -1327,6 +1333,288 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// short sequences (T <= 64: ViT-B/32 has 49 + 1 tokens): two heads per 128-row tile
+// ---------------------------------------------------------------------------------------------------------
+// A 50-token head fills 39 % of a 128-row MMA tile, so one CTA packs heads (2g, 2g+1) of a cutout: rows / keys
+// [0, 64) belong to the first head, [64, 128) to the second (tokens >= T are zero rows from the TMA bounds check).
+// S = Q K^T is then a 128 x 128 tile of which only the two diagonal 64 x 64 blocks mean anything; P is written
+// block-diagonal (zeros elsewhere), so P V, P^T dO, dS^T Q and dS K never mix the heads.  The tensor work is
+// trivial (12 / 32 MMAs per pair); these kernels exist to replace ~40 small dependent mma.sync steps per head by
+// one TMA round trip and a handful of tensor-memory operations.
+constexpr int kPackFwdThreads = 160;  // warps 0-3 softmax (row == TMEM lane), warp 4 TMA + MMA
+constexpr int kPackOffK = 0, kPackOffV = kBlkBytes, kPackOffQ = 2 * kBlkBytes;
+constexpr int kPackFwdOffBar = 3 * kBlkBytes;
+constexpr int kPackFwdSmem = kPackFwdOffBar + 64 + 1024;
+constexpr uint32_t kPackColO = 128;
+
+struct PackParams {
+    int T, heads;
+    const bf16* qkv;
+    bf16* out;
+    float* lse;
+    // backward only
+    const bf16* d_out;
+    const float* delta;
+    bf16* d_qkv;
+};
+
+// both heads' [64 x 64] boxes of one operand (column offset col0 of head h0) into a [128 x 64] tile
+__device__ __forceinline__ void pack_load(const CUtensorMap* map, uint64_t* bar, uint8_t* tile, int col0, int n) {
+    tma_load_3d(map, bar, tile, col0, 0, n, kEvictFirst);
+    tma_load_3d(map, bar, tile + 64 * 128, col0 + kHd, 0, n, kEvictFirst);
+}
+
+__global__ void __launch_bounds__(kPackFwdThreads, 2)
+attn_fwd_pack_kernel(const __grid_constant__ CUtensorMap map_qkv, const PackParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sm_k = sm + kPackOffK;
+    uint8_t* sm_v = sm + kPackOffV;
+    uint8_t* sm_q = sm + kPackOffQ;
+    // mbarriers: 0 operands landed, 1 S ready, 2 P stored, 3 O ready
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kPackFwdOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h0 = 2 * blockIdx.x, n = blockIdx.y;
+    const int T = p.T, D = p.heads * kHd;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            mbar_init(&bars[2], 4);
+            mbar_init(&bars[3], 1);
+            fence_barrier_init();
+            mbar_arrive_expect_tx(&bars[0], 3 * kBlkBytes);
+            pack_load(&map_qkv, &bars[0], sm_q, h0 * kHd, n);
+            pack_load(&map_qkv, &bars[0], sm_k, D + h0 * kHd, n);
+            pack_load(&map_qkv, &bars[0], sm_v, 2 * D + h0 * kHd, n);
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_wait(&bars[0], 0);
+            tc_fence_after();
+            mma_tile_x_rows(tmem, sm_q, sm_k, 128);  // S = Q K^T, both heads at once
+            umma_commit(&bars[1]);
+            mbar_wait(&bars[2], 0);
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+            for (int ks = 0; ks < 8; ++ks)
+                umma_f16_ts(tmem + kPackColO, tmem + ks * 8, umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)), idesc, ks != 0);
+            umma_commit(&bars[3]);
+        }
+    } else {
+        const int r = warp * 32 + lane;  // tile row == TMEM lane
+        const int blk = r >> 6, t = r & 63;
+        const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        mbar_wait(&bars[1], 0);
+        tc_fence_after();
+        uint32_t v[64];
+        tmem_ld_32x32(trow + 64 * blk, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+        tmem_ld_32x32(trow + 64 * blk + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
+        tmem_wait_ld();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, (c < T) ? __uint_as_float(v[c]) : -INFINITY);
+        const float mb = mx * kLog2e;
+        float sum = 0.f;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float e0 = (2 * c < T) ? exp2f(fmaf(__uint_as_float(v[2 * c]), kLog2e, -mb)) : 0.f;
+            const float e1 = (2 * c + 1 < T) ? exp2f(fmaf(__uint_as_float(v[2 * c + 1]), kLog2e, -mb)) : 0.f;
+            sum += e0 + e1;
+            pk[c] = pack_bf16(e0, e1);
+        }
+        // P row: this head's 64 keys as 32 packed columns, zeros for the other head's keys
+        uint32_t zero[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) zero[c] = 0u;
+        tmem_st<16>(trow + 32 * blk, reinterpret_cast<uint32_t(&)[16]>(pk[0]));
+        tmem_st<16>(trow + 32 * blk + 16, reinterpret_cast<uint32_t(&)[16]>(pk[16]));
+        tmem_st<16>(trow + 32 * (1 - blk), zero);
+        tmem_st<16>(trow + 32 * (1 - blk) + 16, zero);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2]);
+        const int h = h0 + blk;
+        if (t < T) p.lse[(static_cast<size_t>(n) * p.heads + h) * T + t] = mx + logf(sum);
+        const float inv = 1.0f / sum;
+        mbar_wait(&bars[3], 0);
+        tc_fence_after();
+        tmem_ld_32x32(trow + kPackColO, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+        tmem_ld_32x32(trow + kPackColO + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
+        tmem_wait_ld();
+        if (t < T) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(n) * T + t) * D + h * kHd);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                dst[g] = make_uint4(pack_bf16(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
+                                    pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
+                                    pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
+                                    pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+constexpr int kPackBwdThreads = 288;  // warps 0-7 elementwise (lane quarter = warp & 3, column half = warp >> 2), 8 TMA + MMA
+constexpr int kPackOffDO = 3 * kBlkBytes;
+constexpr int kPackOffDST = 4 * kBlkBytes;     // dS^T [128 keys x 128 queries], two 64-column blocks
+constexpr int kPackBwdOffVec = 6 * kBlkBytes;  // float lse2[128], delta[128]
+constexpr int kPackBwdOffBar = kPackBwdOffVec + 1024;
+constexpr int kPackBwdSmem = kPackBwdOffBar + 64 + 1024;
+// 256 TMEM columns so that two CTAs share an SM: S^T [0,128) and dP^T [128,256) are dead once the elementwise warps
+// have read them, so P^T (packed bf16, the A operand of dV) goes over S^T [0,64), dQ over S^T [64,128), dV and dK
+// over dP^T.
+constexpr uint32_t kPkST = 0, kPkDPT = 128, kPkPT = 0, kPkDQ = 64, kPkDV = 128, kPkDK = 192;
+
+__global__ void __launch_bounds__(kPackBwdThreads, 2)
+attn_bwd_pack_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                     const PackParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sm_k = sm + kPackOffK;
+    uint8_t* sm_v = sm + kPackOffV;
+    uint8_t* sm_q = sm + kPackOffQ;
+    uint8_t* sm_do = sm + kPackOffDO;
+    uint8_t* sm_dst = sm + kPackOffDST;
+    float* lse2 = reinterpret_cast<float*>(sm + kPackBwdOffVec);
+    float* delta = lse2 + 128;
+    // mbarriers: 0 operands landed, 1 S^T / dP^T ready, 2 P^T / dS^T stored, 3 gradients ready
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kPackBwdOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h0 = 2 * blockIdx.x, n = blockIdx.y;
+    const int T = p.T, D = p.heads * kHd;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            mbar_init(&bars[2], 8);
+            mbar_init(&bars[3], 1);
+            fence_barrier_init();
+            mbar_arrive_expect_tx(&bars[0], 4 * kBlkBytes);
+            pack_load(&map_qkv, &bars[0], sm_k, D + h0 * kHd, n);
+            pack_load(&map_qkv, &bars[0], sm_q, h0 * kHd, n);
+            pack_load(&map_qkv, &bars[0], sm_v, 2 * D + h0 * kHd, n);
+            pack_load(&map_do, &bars[0], sm_do, h0 * kHd, n);
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    } else if (threadIdx.x < 128) {
+        const int blk = threadIdx.x >> 6, t = threadIdx.x & 63;
+        const size_t idx = (static_cast<size_t>(n) * p.heads + h0 + blk) * T + min(t, T - 1);
+        lse2[threadIdx.x] = (t < T) ? p.lse[idx] * kLog2e : INFINITY;  // +inf: p = 0 for queries past the end
+        delta[threadIdx.x] = (t < T) ? p.delta[idx] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_wait(&bars[0], 0);
+            tc_fence_after();
+            mma_tile_x_rows(tmem + kPkST, sm_k, sm_q, 128);    // S^T  = K Q^T
+            mma_tile_x_rows(tmem + kPkDPT, sm_v, sm_do, 128);  // dP^T = V dO^T
+            umma_commit(&bars[1]);
+            mbar_wait(&bars[2], 0);
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+            for (int ks = 0; ks < 8; ++ks)  // dV = P^T dO, A = P^T from tensor memory
+                umma_f16_ts(tmem + kPkDV, tmem + kPkPT + ks * 8, umma_smem_desc_sw128(smem_u32(sm_do + ks * 2048)), idesc,
+                            ks != 0);
+            mma_blocks_x_cols(tmem + kPkDK, sm_dst, sm_q, 8, false);  // dK = dS^T Q
+            mma_rows_t_x_cols(tmem + kPkDQ, sm_dst, sm_k, 8, false);  // dQ = dS K
+            umma_commit(&bars[3]);
+        }
+    } else {
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;  // key row (S^T, dV, dK) / query row (dQ) == TMEM lane
+        const int blk = r >> 6, t = r & 63;
+        const bool row_ok = t < T;
+        const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+        mbar_wait(&bars[1], 0);
+        tc_fence_after();
+        // this head's 64 query columns: this warp takes 32 of them, 16 at a time
+        const int c0 = 64 * blk + 32 * half;
+        uint32_t sa[16], da[16], sb[16], db[16];
+        tmem_ld<16>(trow + kPkST + c0, sa), tmem_ld<16>(trow + kPkDPT + c0, da);
+        tmem_ld<16>(trow + kPkST + c0 + 16, sb), tmem_ld<16>(trow + kPkDPT + c0 + 16, db);
+        // the other head's columns of this row are zero (block-diagonal P^T, dS^T): this warp clears half of them
+        {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            uint8_t* zd = sm_dst + (1 - blk) * kBlkBytes;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(zd + row_chunk(r, 4 * half + g)) = z;
+        }
+        tmem_wait_ld();
+        // P^T overwrites S^T columns that the OTHER column-half warp of this lane quarter may still be reading
+        named_bar_sync(1, 256);
+        const Cols16 oa = bwd_cols16(sa, da, lse2 + c0, delta + c0, row_ok);
+        const Cols16 ob = bwd_cols16(sb, db, lse2 + c0 + 16, delta + c0 + 16, row_ok);
+        bwd_store_ds(oa, sm_dst + blk * kBlkBytes, r, (c0 & 63) >> 3);
+        bwd_store_ds(ob, sm_dst + blk * kBlkBytes, r, ((c0 + 16) & 63) >> 3);
+        {
+            // packed P^T row: queries of head 0 in columns [0, 32), of head 1 in [32, 64)
+            const uint32_t pa[8] = {oa.p[0].x, oa.p[0].y, oa.p[0].z, oa.p[0].w, oa.p[1].x, oa.p[1].y, oa.p[1].z, oa.p[1].w};
+            const uint32_t pb[8] = {ob.p[0].x, ob.p[0].y, ob.p[0].z, ob.p[0].w, ob.p[1].x, ob.p[1].y, ob.p[1].z, ob.p[1].w};
+            uint32_t zero[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) zero[c] = 0u;
+            tmem_st<8>(trow + kPkPT + 32 * blk + 16 * half, pa);
+            tmem_st<8>(trow + kPkPT + 32 * blk + 16 * half + 8, pb);
+            tmem_st<16>(trow + kPkPT + 32 * (1 - blk) + 16 * half, zero);
+        }
+        tmem_wait_st();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2]);
+        mbar_wait(&bars[3], 0);
+        tc_fence_after();
+        bf16* grow = p.d_qkv + (static_cast<size_t>(n) * T + min(t, T - 1)) * 3 * D + (h0 + blk) * kHd + 32 * half;
+        const uint32_t cols[3] = {kPkDQ, kPkDK, kPkDV};
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {
+            uint32_t v[32];
+            tmem_ld<32>(trow + cols[which] + 32 * half, v);  // warp-collective: every lane takes part, valid rows store
+            tmem_wait_ld();
+            if (row_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(grow + which * D);
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    dst[g] = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                        pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                        pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                        pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------
 using EncodeFn = PFN_cuTensorMapEncodeTiled_v12000;
@@ -1342,24 +1630,24 @@ EncodeFn encode_fn() {
     return fn;
 }
 
-// [n][T][cols] bf16 view of a row-major [n*T, cols] matrix; box = {64 columns, 128 rows, 1}.  Rows >= T of a box
-// are zero-filled, so whole 128-row boxes are always loaded.
-int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols) {
+// [n][T][cols] bf16 view of a row-major [n*T, cols] matrix; box = {64 columns, box_rows (128 or 64) rows, 1}.
+// Rows >= T of a box are zero-filled, so whole boxes are always loaded.
+int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols, int box_rows = 128) {
     struct Key {
         const void* p;
-        int n, T, cols;
-        bool operator==(const Key& o) const { return p == o.p && n == o.n && T == o.T && cols == o.cols; }
+        int n, T, cols, box;
+        bool operator==(const Key& o) const { return p == o.p && n == o.n && T == o.T && cols == o.cols && box == o.box; }
     };
     struct Hash {
         size_t operator()(const Key& k) const {
             size_t h = reinterpret_cast<size_t>(k.p);
-            for (int v : {k.n, k.T, k.cols}) h = h * 1000003u ^ static_cast<size_t>(v);
+            for (int v : {k.n, k.T, k.cols, k.box}) h = h * 1000003u ^ static_cast<size_t>(v);
             return h;
         }
     };
     static std::mutex mu;
     static std::unordered_map<Key, CUtensorMap, Hash> cache;
-    const Key key{ptr, n, T, cols};
+    const Key key{ptr, n, T, cols, box_rows};
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
@@ -1372,7 +1660,7 @@ int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols) {
     if (encode == nullptr) return set_error(-2, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(n)};
     const cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(cols) * 2 * T};
-    const cuuint32_t box[3] = {64, 128, 1};
+    const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1388,6 +1676,11 @@ int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols) {
 // T - 1 <= 256: everything in tensor memory at once (forward) / one fused backward; beyond that the streaming forward.
 bool use_tc(int T) { return T >= 66 && T <= 257; }
 bool use_flash_fwd(int T) { return T > 257; }
+bool g_pack_enabled = []() {  // PCG_ATTN_PACK=1 until the packed kernels have passed the GPU suite
+    const char* e = getenv("PCG_ATTN_PACK");
+    return e != nullptr && e[0] == '1';
+}();
+bool use_pack(int T, int heads) { return g_pack_enabled && T <= 64 && heads % 2 == 0; }  // two heads per 128-row tile
 bool use_long_bwd(int T) { return T > 257 && T <= kLongMaxT; }
 size_t bwd_delta_floats(int n, int T, int heads) { return align_up(static_cast<size_t>(n) * heads * T, 64); }
 
@@ -1427,8 +1720,21 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "pcg_attn_fwd: n and heads must be <= 65535");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ProfileScope prof(PCG_PROF_ATTN_FWD, 4.0 * T * T * kHd * heads * n, s);
-    if (g_force_legacy || !(use_tc(T) || use_flash_fwd(T))) return attn_fwd_legacy(qkv, out, lse, n, T, heads, 0, s);
     const int D = heads * kHd;
+    if (!g_force_legacy && use_pack(T, heads)) {
+        CUtensorMap pmap;
+        if (int rc = make_map3(&pmap, qkv, n, T, 3 * D, 64)) return rc;
+        static bool pack_configured = false;
+        if (!pack_configured) {
+            PCG_CUDA(cudaFuncSetAttribute(attn_fwd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackFwdSmem));
+            pack_configured = true;
+        }
+        PackParams pp{T, heads, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, nullptr, nullptr, nullptr};
+        attn_fwd_pack_kernel<<<dim3(heads / 2, n), kPackFwdThreads, kPackFwdSmem, s>>>(pmap, pp);
+        PCG_LAUNCH_CHECK("attn_fwd_pack_kernel");
+        return 0;
+    }
+    if (g_force_legacy || !(use_tc(T) || use_flash_fwd(T))) return attn_fwd_legacy(qkv, out, lse, n, T, heads, 0, s);
     CUtensorMap map;
     if (int rc = make_map3(&map, qkv, n, T, 3 * D)) return rc;
     if (use_flash_fwd(T)) {
@@ -1471,6 +1777,22 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ProfileScope prof(PCG_PROF_ATTN_BWD, 8.0 * T * T * kHd * heads * n, s);
     const int D = heads * kHd;
+    if (!g_force_legacy && use_pack(T, heads)) {
+        CUtensorMap pmap, pmap_do;
+        if (int rc = make_map3(&pmap, qkv, n, T, 3 * D, 64)) return rc;
+        if (int rc = make_map3(&pmap_do, d_out, n, T, D, 64)) return rc;
+        static bool pack_configured = false;
+        if (!pack_configured) {
+            PCG_CUDA(cudaFuncSetAttribute(attn_bwd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackBwdSmem));
+            pack_configured = true;
+        }
+        if (int rc = attn_delta(out, d_out, delta_ws, n, T, heads, s)) return rc;
+        PackParams pp{T, heads, static_cast<const bf16*>(qkv), nullptr, const_cast<float*>(lse),
+                      static_cast<const bf16*>(d_out), delta_ws, static_cast<bf16*>(d_qkv)};
+        attn_bwd_pack_kernel<<<dim3(heads / 2, n), kPackBwdThreads, kPackBwdSmem, s>>>(pmap, pmap_do, pp);
+        PCG_LAUNCH_CHECK("attn_bwd_pack_kernel");
+        return 0;
+    }
     if (!g_force_legacy && use_long_bwd(T)) {
         CUtensorMap lmap, lmap_do;
         if (int rc = make_map3(&lmap, qkv, n, T, 3 * D)) return rc;

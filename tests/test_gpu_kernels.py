@@ -171,12 +171,13 @@ def attn_reference(qkv, n, t, heads):
 @pytest.mark.parametrize("n,t,heads", [(2, 50, 12), (1, 197, 12), (3, 257, 16), (1, 577, 16), (2, 17, 2), (1, 64, 2),
                                        (1, 65, 2), (2, 128, 1), (2, 256, 4), (1, 272, 2), (1, 130, 2), (2, 192, 3),
                                        (5, 257, 3), (1, 200, 1), (1, 66, 1), (1, 129, 2), (2, 145, 2), (1, 241, 1),
-                                       (2, 113, 2), (1, 258, 2), (2, 400, 3), (1, 385, 1), (3, 577, 2), (1, 1025, 1)])
+                                       (2, 113, 2), (1, 258, 2), (2, 400, 3), (1, 385, 1), (3, 577, 2), (1, 1025, 1),
+                                       (3, 50, 4), (1, 33, 4), (1, 2, 2), (2, 64, 6), (1, 50, 1), (2, 16, 2)])
 @pytest.mark.parametrize("tc", [0, 1])
 def test_attention(cuda_device, n, t, heads, tc):
     """tc=1 routes T >= 66 through the tcgen05 kernels (the default; T > 257 streams the keys with an online
-    softmax: 258 / 385 leave one key in the last chunk, 400 fifteen, 1025 fills eight chunks), tc=0 through the
-    mma.sync kernels."""
+    softmax: 258 / 385 leave one key in the last chunk, 400 fifteen, 1025 fills eight chunks; T <= 64 with an even
+    head count packs two heads per tile, an odd head count stays on mma.sync), tc=0 through the mma.sync kernels."""
     native.lib().pcg_attn_set_legacy(0 if tc else 1)
     d = heads * 64
     g = torch.Generator(device="cpu").manual_seed(t + heads)
