@@ -1676,9 +1676,9 @@ int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols, int box
 // T - 1 <= 256: everything in tensor memory at once (forward) / one fused backward; beyond that the streaming forward.
 bool use_tc(int T) { return T >= 66 && T <= 257; }
 bool use_flash_fwd(int T) { return T > 257; }
-bool g_pack_enabled = []() {  // PCG_ATTN_PACK=1 until the packed kernels have passed the GPU suite
+bool g_pack_enabled = []() {  // PCG_ATTN_PACK=0 sends T <= 64 back to the mma.sync kernels
     const char* e = getenv("PCG_ATTN_PACK");
-    return e != nullptr && e[0] == '1';
+    return !(e != nullptr && e[0] == '0');
 }();
 bool use_pack(int T, int heads) { return g_pack_enabled && T <= 64 && heads % 2 == 0; }  // two heads per 128-row tile
 bool use_long_bwd(int T) { return T > 257 && T <= kLongMaxT; }
