@@ -178,3 +178,25 @@ def test_schedule_ts_and_glue_host_logic_match_reference_golden():
     assert checkpoint.detached.grad is not None
     checkpoint.continue_backward()
     assert images.grad is not None and torch.allclose(images.grad, torch.full_like(images, 2.0 / images.numel()))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one) on a one-cutout sample: one JSON
+    line with the contract's keys, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "1", "--workload", "vit_b32_224_16cut_256px"], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "cutouts/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
+    assert d["config"]["workload"] == "vit_b32_224_16cut_256px" and d["metric"].startswith("CLIP-guidance cutouts/sec")
