@@ -60,7 +60,9 @@ __device__ __forceinline__ uint32_t row_chunk(int row, int chunk) {
 }
 
 // dot product of a swizzled smem row (64 bf16) with a float[64] vector in shared memory (4 independent chains)
-__device__ __forceinline__ float row_dot(const uint8_t* mat, int row, const float* vec) {
+// (not inlined, like edge_gemv below: the 256 + 1 kernels are instruction-cache bound -- ncu: 17 % of stalls are
+// no_instructions -- and these run off the critical path; inlining them made the forward 9 % slower)
+__device__ __noinline__ float row_dot(const uint8_t* mat, int row, const float* vec) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -100,7 +102,7 @@ __device__ __forceinline__ void load_row_f32(float* dst, const bf16* src, int la
 // out[0..63] = (sum_i coef[i] * mat[i][.] + corner * xrow[.]) * scale as bf16, one warp.  mat = swizzled smem rows,
 // coef / xrow = float vectors in shared memory.  Lane = (row group lane >> 3, 16-byte chunk lane & 7): the four row
 // groups each walk a quarter of the rows with 8 independent accumulators and are summed by two shuffles at the end.
-__device__ __forceinline__ void edge_gemv(const float* coef, const uint8_t* mat, int rows, float corner,
+__device__ __noinline__ void edge_gemv(const float* coef, const uint8_t* mat, int rows, float corner,
                                           const float* xrow, bf16* gdst, float scale, int lane) {
     const int kg = lane >> 3, ch = lane & 7;
     float acc[8];
