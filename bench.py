@@ -31,6 +31,8 @@ WORKLOADS = {
     "vit_l14_224_128cut_512px": ("ViT-L-14", 512, 128, 128, 1),
     "vit_b32_224_64cut_4x512px": ("ViT-B-32", 512, 64, 64, 4),
     "vit_l14_336_256cut_768px": ("ViT-L-14-336", 768, 256, 192, 1),
+    # BASELINE configs[3] as written: ONE 768x768 image, 256 cutouts in total, sharded over the ranks (strong scaling)
+    "vit_l14_336_256cut_768px_1image": ("ViT-L-14-336", 768, 256, 192, 0),
     "vit_b32_224_16cut_256px": ("ViT-B-32", 256, 16, 64, 1),
 }
 DEFAULT_WORKLOAD = "vit_l14_224_128cut_512px"
@@ -194,7 +196,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
 
     arch, hw, n_cut, min_size, imgs_per_gpu = WORKLOADS[args.workload]
     shape = SHAPES[arch]
-    n_images = imgs_per_gpu * world
+    n_images = imgs_per_gpu * world if imgs_per_gpu > 0 else 1  # 0: one image in total, its cutouts sharded
     cutouts_per_step = n_images * n_cut
 
     loss_mod = losses.CLIP(arch, n_cutouts=n_cut, min_size=min_size, max_size=hw, seed=0, process_group=group)
@@ -288,7 +290,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
     cpu_value, cpu_med, cpu_done = time_cpu(arch, hw, min_size, args.cpu_sample, 2, 1) if not args.no_cpu else (None, None, 0)
     line = {
         "metric": METRIC, "value": value, "unit": "cutouts/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak" if imgs_per_gpu > 0 else "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "model": arch, "images": n_images, "image": f"{hw}x{hw}",
                    "cutouts_per_image": n_cut, "cutouts_per_step": cutouts_per_step, "targets": 2,
