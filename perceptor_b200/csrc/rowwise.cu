@@ -274,8 +274,11 @@ head_ln_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, cons
 }
 
 // C[n, N] = A[n, K] @ B with B = Bm[K, N] (kTransB = false) or B = Bm[N, K]^T (kTransB = true), fp32 on the CUDA
-// cores: 16 x 64 tile per CTA, 32-deep K chunks through shared memory, thread = 1 row x 4 columns.
-constexpr int kHgRows = 16, kHgCols = 64, kHgK = 32;
+// cores: 16 x 64 tile per CTA, 32-deep K chunks through shared memory, thread = 1 row x 4 columns.  The problem is
+// tiny (128 x 768 x 1024 for ViT-L/14) and latency bound, so K is split kHgParts ways over blockIdx.z to put four
+// times as many CTAs to work; part z writes its partial sums to C + z * n * N and the consumer kernel adds them up
+// (a fixed order: deterministic, unlike atomics).
+constexpr int kHgRows = 16, kHgCols = 64, kHgK = 32, kHgParts = 4;
 template <bool kTransB>
 __global__ void __launch_bounds__(kHeadThreads)
 head_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int n, int N, int K) {
@@ -284,19 +287,22 @@ head_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, floa
     const int tid = threadIdx.x;
     const int n0 = blockIdx.y * kHgRows, c0 = blockIdx.x * kHgCols;
     const int row = tid >> 4, col = (tid & 15) * 4;
+    const int k_per = ((K + kHgParts - 1) / kHgParts + kHgK - 1) / kHgK * kHgK;
+    const int k_begin = blockIdx.z * k_per, k_end = min(K, k_begin + k_per);
+    C += static_cast<size_t>(blockIdx.z) * n * N;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < K; k0 += kHgK) {
+    for (int k0 = k_begin; k0 < k_end; k0 += kHgK) {
         for (int i = tid; i < kHgRows * kHgK; i += kHeadThreads) {
             const int r = i / kHgK, k = i - r * kHgK;
-            As[r][k] = (n0 + r < n && k0 + k < K) ? A[static_cast<size_t>(n0 + r) * K + k0 + k] : 0.f;
+            As[r][k] = (n0 + r < n && k0 + k < k_end) ? A[static_cast<size_t>(n0 + r) * K + k0 + k] : 0.f;
         }
         for (int i = tid; i < kHgK * kHgCols; i += kHeadThreads) {
             if (kTransB) {  // Bm rows index the output column, contiguous along k
                 const int c = i / kHgK, k = i - c * kHgK;
-                Bs[k][c] = (c0 + c < N && k0 + k < K) ? __ldg(Bm + static_cast<size_t>(c0 + c) * K + k0 + k) : 0.f;
+                Bs[k][c] = (c0 + c < N && k0 + k < k_end) ? __ldg(Bm + static_cast<size_t>(c0 + c) * K + k0 + k) : 0.f;
             } else {
                 const int k = i / kHgCols, c = i - k * kHgCols;
-                Bs[k][c] = (c0 + c < N && k0 + k < K) ? __ldg(Bm + static_cast<size_t>(k0 + k) * N + c0 + c) : 0.f;
+                Bs[k][c] = (c0 + c < N && k0 + k < k_end) ? __ldg(Bm + static_cast<size_t>(k0 + k) * N + c0 + c) : 0.f;
             }
         }
         __syncthreads();
@@ -318,10 +324,22 @@ head_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, floa
     }
 }
 
+// row `n` of a split-K result: add parts 1 .. kHgParts-1 into part 0 (each CTA owns one row)
+__device__ __forceinline__ void combine_parts(float* base, int n_rows, int width, int n) {
+    float* r0 = base + static_cast<size_t>(n) * width;
+    for (int e = threadIdx.x; e < width; e += kHeadThreads) {
+        float v = r0[e];
+#pragma unroll
+        for (int q = 1; q < kHgParts; ++q) v += base[(static_cast<size_t>(q) * n_rows + n) * width + e];
+        r0[e] = v;
+    }
+    __syncthreads();
+}
+
 // e = z / |z| (or z), spherical-distance loss against every target and dz = d(loss * scale)/dz (or the pull-back of
 // an upstream gradient d_enc through the normalisation)
 __global__ void __launch_bounds__(kHeadThreads)
-head_dist_kernel(const float* __restrict__ z, const float* __restrict__ targets, const float* __restrict__ tweights,
+head_dist_kernel(float* __restrict__ z, const float* __restrict__ targets, const float* __restrict__ tweights,
                  int E, int M, float scale, int normalize, float* __restrict__ loss_sum, float* __restrict__ enc_out,
                  const float* __restrict__ d_enc, float* __restrict__ dz) {
     extern __shared__ float sm[];
@@ -329,6 +347,7 @@ head_dist_kernel(const float* __restrict__ z, const float* __restrict__ targets,
     float* gbuf = sm + E;  // [E] d/de
     __shared__ float red[kHeadThreads / 32];
     const int n = blockIdx.x, tid = threadIdx.x;
+    combine_parts(z, gridDim.x, E, n);  // z arrives as kHgParts split-K partials
     const float* zr = z + static_cast<size_t>(n) * E;
     float zz = 0.f;
     for (int e = tid; e < E; e += kHeadThreads) zz += zr[e] * zr[e];
@@ -377,10 +396,11 @@ head_dist_kernel(const float* __restrict__ z, const float* __restrict__ targets,
 
 // dx[CLS row] = ln_post'(dy): statistics recomputed from x (one 4 KB row)
 __global__ void __launch_bounds__(kHeadThreads)
-head_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, const float* __restrict__ dy, int T, int D,
+head_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, float* __restrict__ dy, int T, int D,
                    float* __restrict__ dx, bf16* __restrict__ dx_bf16) {
     __shared__ float red[kHeadThreads / 32];
     const int n = blockIdx.x, tid = threadIdx.x;
+    combine_parts(dy, gridDim.x, D, n);  // dy arrives as kHgParts split-K partials
     const float* xr = x + static_cast<size_t>(n) * T * D;
     const float* gr = dy + static_cast<size_t>(n) * D;
     float s = 0.f;
@@ -477,7 +497,8 @@ extern "C" int pcg_embed_bwd(const float* dx0, const void* dx0_bf16, const float
 
 extern "C" size_t pcg_head_workspace_bytes(int n, int D, int E) {
     if (n <= 0 || D <= 0 || E <= 0) return 0;
-    return (2 * static_cast<size_t>(n) * D + 2 * static_cast<size_t>(n) * E) * sizeof(float);
+    // y [n,D], dy [parts][n,D], z [parts][n,E], dz [n,E]
+    return (static_cast<size_t>(n) * D * (1 + kHgParts) + static_cast<size_t>(n) * E * (1 + kHgParts)) * sizeof(float);
 }
 
 extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_b, const float* proj,
@@ -493,15 +514,15 @@ extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_
     const size_t smem = static_cast<size_t>(2 * E) * sizeof(float);
     PCG_CHECK_ARG(smem <= 48 * 1024, "pcg_head_loss: E=%d exceeds the shared-memory budget", E);
     ProfileScope prof(PCG_PROF_HEAD, ((dx ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0)) * n * T * D + (want_dx ? 4.0 : 2.0) * n * D * E, s);
-    float* y = workspace;                             // [n, D] ln_post output
-    float* dy = y + static_cast<size_t>(n) * D;       // [n, D]
-    float* z = dy + static_cast<size_t>(n) * D;       // [n, E]
-    float* dz = z + static_cast<size_t>(n) * E;       // [n, E]
+    float* y = workspace;                                        // [n, D] ln_post output
+    float* dy = y + static_cast<size_t>(n) * D;                  // [parts][n, D]
+    float* z = dy + static_cast<size_t>(n) * D * kHgParts;       // [parts][n, E]
+    float* dz = z + static_cast<size_t>(n) * E * kHgParts;       // [n, E]
     if (dx != nullptr) PCG_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(n) * T * D * sizeof(float), s));
     if (dx_bf16 != nullptr) PCG_CUDA(cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(n) * T * D * 2, s));
     head_ln_kernel<<<n, kHeadThreads, 0, s>>>(x, ln_g, ln_b, T, D, y);
     PCG_LAUNCH_CHECK("head_ln_kernel");
-    head_gemm_kernel<false><<<dim3(ceil_div(E, kHgCols), ceil_div(n, kHgRows)), kHeadThreads, 0, s>>>(y, proj, z, n, E, D);
+    head_gemm_kernel<false><<<dim3(ceil_div(E, kHgCols), ceil_div(n, kHgRows), kHgParts), kHeadThreads, 0, s>>>(y, proj, z, n, E, D);
     PCG_LAUNCH_CHECK("head_gemm_kernel");
     const bool has_loss = targets != nullptr && M > 0;
     if (!has_loss && d_enc == nullptr && enc_out == nullptr) return 0;
@@ -509,7 +530,7 @@ extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_
                                                    normalize, loss_sum, enc_out, d_enc, want_dx ? dz : nullptr);
     PCG_LAUNCH_CHECK("head_dist_kernel");
     if (!want_dx) return 0;
-    head_gemm_kernel<true><<<dim3(ceil_div(D, kHgCols), ceil_div(n, kHgRows)), kHeadThreads, 0, s>>>(dz, proj, dy, n, D, E);
+    head_gemm_kernel<true><<<dim3(ceil_div(D, kHgCols), ceil_div(n, kHgRows), kHgParts), kHeadThreads, 0, s>>>(dz, proj, dy, n, D, E);
     PCG_LAUNCH_CHECK("head_gemm_kernel");
     head_ln_bwd_kernel<<<n, kHeadThreads, 0, s>>>(x, ln_g, dy, T, D, dx, static_cast<bf16*>(dx_bf16));
     PCG_LAUNCH_CHECK("head_ln_bwd_kernel");
