@@ -109,6 +109,7 @@ __device__ __forceinline__ void store_tile_bf16(const float (&acc)[8][4], bf16* 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                        float* __restrict__ lse, int T, int heads, int q_begin) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     __shared__ __align__(128) bf16 sQ[kTile * kHd];
     __shared__ __align__(128) bf16 sK[2][kTile * kHd];
     __shared__ __align__(128) bf16 sV[2][kTile * kHd];
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
                                                           const float* __restrict__ lse,
                                                           const float* __restrict__ delta, bf16* __restrict__ d_qkv,
                                                           int T, int heads, int q_begin) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ __align__(128) uint8_t smem_dyn[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_dyn);  // kv[] holds Q / dO here; q[] / d_o[] hold K / V tiles
 

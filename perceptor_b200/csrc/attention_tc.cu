@@ -275,6 +275,7 @@ __device__ __forceinline__ float fwd_row_exp(uint32_t trow, int c_begin, int c_e
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams p) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -509,6 +510,7 @@ enum { kFbK = 0, kFbV = 2, kFbS = 4, kFbP = 5, kFbO = 6, kFbX = 7 };
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams p) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -791,6 +793,7 @@ __device__ __forceinline__ float chunk_dot(const uint4& x, const uint4& y) {
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                    const BwdParams p) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -1130,6 +1133,7 @@ struct LongParams {
 __global__ void __launch_bounds__(kLongThreads, 1)
 attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                      const LongParams p) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -1323,6 +1327,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 // dQ sums (f32 [rows, D]) -> the q third of d_qkv (bf16 [rows, 3D]); 8 elements per thread
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ dq, bf16* __restrict__ d_qkv,
                                                               size_t rows, int D) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int per_row = D >> 3;
     if (idx >= rows * per_row) return;
@@ -1368,6 +1373,7 @@ __device__ __forceinline__ void pack_load(const CUtensorMap* map, uint64_t* bar,
 
 __global__ void __launch_bounds__(kPackFwdThreads, 2)
 attn_fwd_pack_kernel(const __grid_constant__ CUtensorMap map_qkv, const PackParams p) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -1487,6 +1493,7 @@ constexpr uint32_t kPkST = 0, kPkDPT = 128, kPkPT = 0, kPkDQ = 64, kPkDV = 128, 
 __global__ void __launch_bounds__(kPackBwdThreads, 2)
 attn_bwd_pack_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                      const PackParams p) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);

@@ -146,6 +146,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();  // barriers visible to the peer before use
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's tail;
+    // nothing below may read what it produced before it has completed
+    grid_dep_wait();
+    grid_dep_launch();
 
     if (warp == kWarpTma) {
         // ===================== TMA producer (one thread) =====================
@@ -403,6 +407,11 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
     return 0;
 }
 
+bool g_pdl_enabled = []() {
+    const char* e = getenv("PCG_PDL");
+    return e != nullptr && e[0] == '1';
+}();
+
 template <int BN, int MODE, int ACT, int CTAS>
 int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
     using Cfg = TileCfg<BN, CTAS>;
@@ -415,23 +424,28 @@ int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     const int tiles = ceil_div(p.M, BM * CTAS) * ceil_div(p.N, BN);
     const int slots = sm_count() / CTAS;  // clusters (or CTAs) that run concurrently
     const int grid = (tiles < slots ? tiles : slots) * CTAS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
     if constexpr (CTAS == 2) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = Cfg::kSmem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        PCG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>, ma, mb, p));
-    } else {
-        gemm_tcgen05_kernel<BN, MODE, ACT, CTAS><<<grid, kThreads, Cfg::kSmem, stream>>>(ma, mb, p);
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = 2;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
     }
+    if (g_pdl_enabled) {  // start this grid's prologue under the previous kernel's tail (see grid_dep_wait)
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    PCG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>, ma, mb, p));
     PCG_LAUNCH_CHECK("gemm_tcgen05_kernel");
     return 0;
 }

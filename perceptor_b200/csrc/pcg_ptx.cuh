@@ -220,6 +220,13 @@ __device__ __forceinline__ void tma_prefetch_3d(const void* desc, int32_t c0, in
                  "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start while its
+// predecessor in the stream is still draining; grid_dep_wait() blocks until every predecessor grid has completed and
+// its writes are visible (a no-op for a normal launch), grid_dep_launch() lets the successor's CTAs be scheduled as
+// soon as this grid's CTAs free their SMs.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major (cute::UMMA::InstrDescriptor

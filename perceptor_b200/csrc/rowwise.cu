@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float*
                                                                     const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, bf16* __restrict__ y,
                                                                     int rows) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     constexpr int D = NV * 128;
     const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const bf16* 
                                                                     const float* __restrict__ gamma,
                                                                     float* __restrict__ dx_io, bf16* __restrict__ dx_bf16,
                                                                     int rows) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     constexpr int D = NV * 128;
     const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(kRowThreads) embed_fwd_kernel(const float* __r
                                                                 const float* __restrict__ cls, const float* __restrict__ pos,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 float* __restrict__ vout, float* __restrict__ x0, int n, int T) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     constexpr int D = NV * 128;
     const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -398,6 +401,7 @@ head_dist_kernel(float* __restrict__ z, const float* __restrict__ targets, const
 __global__ void __launch_bounds__(kHeadThreads)
 head_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_g, float* __restrict__ dy, int T, int D,
                    float* __restrict__ dx, bf16* __restrict__ dx_bf16) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     __shared__ float red[kHeadThreads / 32];
     const int n = blockIdx.x, tid = threadIdx.x;
     combine_parts(dy, gridDim.x, D, n);  // dy arrives as kHgParts split-K partials

@@ -69,6 +69,7 @@ __device__ __forceinline__ Cut load_cut(const SamplerParams& p, int n) {
 
 __global__ void __launch_bounds__(kThreads) sampler_fwd_kernel(const SamplerParams p, bf16* __restrict__ patches,
                                                                float* __restrict__ out_f32) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ float tmp[];  // [RB][sw]
     const int n = blockIdx.z, ch = blockIdx.y, r0 = blockIdx.x * p.RB;
     const int nr = min(p.RB, p.R - r0);
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(kThreads) sampler_bwd_kernel(const SamplerPara
 // weights transposed, wT[t * (R + 1) + c] (the +1 keeps (t + 1, c) and (t, c + 1) in different banks)
 __global__ void __launch_bounds__(kThreads) sampler_fwd_vec_kernel(const SamplerParams p, bf16* __restrict__ patches,
                                                                    float* __restrict__ out_f32) {
+    grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     extern __shared__ float4 smem4[];
     float* tmp = reinterpret_cast<float*>(smem4);
     const int RS = p.RS;
