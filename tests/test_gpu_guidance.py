@@ -94,6 +94,29 @@ def test_vit_l14_matches_oracle(cuda_device):
     assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
 
 
+def test_vit_l14_336_matches_oracle(cuda_device):
+    """ViT-L/14 @336 (configs[3] shape: T = 577, the streaming forward and key-tile backward attention kernels inside
+    the whole path) on a 400 x 432 image, 3 cutouts."""
+    shape = SHAPES["ViT-L-14-336"]
+    g = torch.Generator().manual_seed(2)
+    images = torch.rand(1, 3, 400, 432, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(5), 1, 400, 432, 3, 1.0, 150, 400)
+    loss, loss_ref, grad, grad_ref, _ = run_case(cuda_device, shape, images, rows.tolist(), multiplier=0.01)
+    assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+    assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
+
+
+def test_vit_b16_matches_oracle(cuda_device):
+    """ViT-B/16 (T = 197: a full and a partly filled 128-row tile in the 256 + 1 attention kernels)."""
+    shape = SHAPES["ViT-B-16"]
+    g = torch.Generator().manual_seed(4)
+    images = torch.rand(2, 3, 200, 260, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(6), 2, 200, 260, 2, 1.0, 64, 200)
+    loss, loss_ref, grad, grad_ref, _ = run_case(cuda_device, shape, images, rows.tolist())
+    assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+    assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
+
+
 def test_whole_image_mode_is_reference_behaviour(cuda_device):
     """n_cutouts=None: every whole (non-square) image is resized, exactly what the reference does."""
     g = torch.Generator().manual_seed(2)
