@@ -117,6 +117,34 @@ def test_vit_b16_matches_oracle(cuda_device):
     assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
 
 
+def test_exact_gelu_towers_match_oracle(cuda_device):
+    """LAION-weight OpenCLIP towers use nn.GELU instead of QuickGELU: same path, other epilogue."""
+    sd = perturb(random_state_dict(TINY, 8))
+    g = torch.Generator().manual_seed(8)
+    images = torch.rand(1, 3, 64, 48, generator=g)
+    rows = [(0, 0, 0, 48), (0, 10, 3, 40), (0, 30, 12, 33)]
+    targets = torch.nn.functional.normalize(torch.randn(2, TINY.embed, generator=g))
+    tw = torch.tensor([1.0, 0.7])
+    img_ref = images.clone().requires_grad_()
+    loss_ref = guidance_oracle.guidance_loss(img_ref, rows, sd, TINY.image_size, TINY.patch, TINY.layers, TINY.heads,
+                                             targets, tw, 1.0, act="gelu")
+    loss_ref.backward()
+    eng = GuidanceEngine(TINY, sd, cuda_device, native.ACT_GELU)
+    img = images.to(cuda_device).requires_grad_()
+    loss = GuidanceLossFn.apply(img, eng, eng.plan_cutouts(np.asarray(rows, dtype=np.int32)), targets.to(cuda_device),
+                                tw.to(cuda_device), 1.0, None)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= LOSS_RTOL * abs(float(loss_ref.detach()))
+    assert cosine(img.grad.cpu(), img_ref.grad) >= GRAD_COS
+    # and the QuickGELU engine on the same weights gives a different answer (the switch is live)
+    eng_q = GuidanceEngine(TINY, sd, cuda_device, native.ACT_QUICKGELU)
+    loss_q = GuidanceLossFn.apply(images.to(cuda_device), eng_q, eng_q.plan_cutouts(np.asarray(rows, dtype=np.int32)),
+                                  targets.to(cuda_device), tw.to(cuda_device), 1.0, None)
+    assert abs(float(loss_q) - float(loss.detach())) > 1e-4 * abs(float(loss.detach()))
+    assert losses.OpenCLIP("ViT-L-14", "laion2b_s32b_b82k").model.act == native.ACT_GELU
+    assert losses.OpenCLIP("ViT-L-14", "openai").model.act == native.ACT_QUICKGELU
+
+
 def test_whole_image_mode_is_reference_behaviour(cuda_device):
     """n_cutouts=None: every whole (non-square) image is resized, exactly what the reference does."""
     g = torch.Generator().manual_seed(2)
