@@ -922,6 +922,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             mma_tile_x_rows(tmem + kColST, sm_k, sm_q, width(0));    // S^T  = K_0 Q_0^T
             mma_tile_x_rows(tmem + kColDPT, sm_v, sm_do, width(0));  // dP^T = V_0 dO_0^T
             umma_commit(&bars[2]);
+            PCG_TRACE(21);
             if (nt > 1) {
                 mbar_arrive_expect_tx(&bars[1], 4 * kBlkBytes);
                 tma_load_3d(&map_qkv, &bars[1], sm_q + kBlkBytes, h * kHd, 128, n, kEvictFirst);

@@ -15,7 +15,7 @@ FWD = {0: "start", 1: "setup done", 2: "K+Q landed", 3: "V landed", 4: "S ready 
 BWD = {0: "start", 1: "first loads landed", 2: "edge vectors ready", 3: "edge gemv done", 4: "b0 S/dP ready", 5: "b0 alu done",
        6: "b1 S/dP ready", 7: "b1 alu done", 8: "b2 S/dP ready", 9: "b2 alu done", 10: "b3 S/dP ready", 11: "b3 alu done",
        12: "tile0 mma done", 13: "tile1 mma done", 14: "epilogues done", 15: "all warps done", 16: "ctl b0 P/dS seen",
-       17: "ctl b1 P/dS seen", 18: "ctl b2 P/dS seen", 19: "ctl b3 P/dS seen", 20: "delta done"}
+       17: "ctl b1 P/dS seen", 18: "ctl b2 P/dS seen", 19: "ctl b3 P/dS seen", 20: "delta done", 21: "ctl issued first S/dP"}
 
 
 def show(trace, names, title):
