@@ -673,13 +673,15 @@ constexpr int kBwdOffQ = 0;
 constexpr int kBwdOffK = 2 * kBlkBytes;
 constexpr int kBwdOffV = 4 * kBlkBytes;
 constexpr int kBwdOffDO = 6 * kBlkBytes;
-constexpr int kBwdOffPT = 8 * kBlkBytes;      // P^T  [128 keys x 128 queries] bf16, two 64-column blocks
-constexpr int kBwdOffDST = 10 * kBlkBytes;    // dS^T, same layout
+// dS^T [128 keys x 128 queries] bf16 as two 64-column blocks, TWO buffers (block parity): dQ(b) reads one while the
+// elementwise warps fill the other for block b + 1.  P^T does not live in shared memory: it is written back over the
+// S^T columns of tensor memory as packed bf16 and read by dV = P^T dO as a TMEM A operand.
+constexpr int kBwdOffDST = 8 * kBlkBytes;
 constexpr int kBwdOffStage = 12 * kBlkBytes;  // 8 warps x [32 rows x 64 B] epilogue staging
 constexpr int kBwdOffVec = 13 * kBlkBytes;    // float[256] x 6: lse2, delta, pcol, dscol, prow, dsrow
 constexpr int kBwdOffX = kBwdOffVec + 6 * 1024;  // float[64] x 4: q_x, k_x, v_x, dO_x; then 8 scalars
 constexpr int kBwdOffBar = kBwdOffX + 4 * 256 + 32;
-constexpr int kBwdSmemBytes = kBwdOffBar + 64 + 1024;
+constexpr int kBwdSmemBytes = kBwdOffBar + 128 + 1024;
 constexpr uint32_t kColST = 0, kColDPT = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
 
 struct BwdParams {
@@ -801,7 +803,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     uint8_t* sm_k = sm + kBwdOffK;
     uint8_t* sm_v = sm + kBwdOffV;
     uint8_t* sm_do = sm + kBwdOffDO;
-    uint8_t* sm_pt = sm + kBwdOffPT;
     uint8_t* sm_dst = sm + kBwdOffDST;
     float* lse2 = reinterpret_cast<float*>(sm + kBwdOffVec);  // lse * log2(e), +inf past the last tensor-core query
     float* delta = lse2 + 256;   // rowsum(dO * O)
@@ -814,10 +815,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     float* vx = qx + 128;
     float* dox = qx + 192;
     float* scal = qx + 256;  // [0] p_xx, [1] ds_xx, [2] lse2_x, [3] delta_x
-    // mbarriers: 0 first block's operands landed, 1 all operands landed, 2 S^T / dP^T ready, 3 / 4 P^T and dS^T
-    // columns [0, 64) / [64, 128) of the block stored, 5 key tile's MMAs done, 6 edge vectors ready
+    // mbarriers: 0 first block's operands landed, 1 all operands landed, 2 S^T / dP^T ready, 3 / 4 first / second half
+    // of every warp's P^T and dS^T columns stored, 5 dV_j / dK_j complete, 6 edge vectors ready, 7 every dQ MMA retired
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kBwdOffBar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, n = blockIdx.y;
@@ -864,6 +865,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             mbar_init(&bars[4], 8);
             mbar_init(&bars[5], 1);
             mbar_init(&bars[6], 3);
+            mbar_init(&bars[7], 1);
             fence_barrier_init();
             mbar_arrive_expect_tx(&bars[0], 4 * kBlkBytes);
             tma_load_3d(&map_qkv, &bars[0], sm_k, D + h * kHd, 0, n, kEvictFirst);
@@ -933,33 +935,47 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             prefetch_next();  // (behind this head's own loads: 276 -> 269 us per layer)
             mbar_wait(&bars[1], 0);
             tc_fence_after();
+            // MMA order per block b: dV / dK on the K-steps whose P^T / dS^T columns are stored (first halves, then second
+            // halves) -> S^T, dP^T of block b + 1 -> dQ of block b.  The next block's scores are queued AHEAD of dQ(b) so
+            // that the elementwise warps start on them while dQ(b), which reads the other dS^T buffer, still runs; the
+            // tensor pipe retires in order, so whatever read the P^T columns or the dS^T buffer about to be refilled
+            // is done by the time S^T(b + 1) signals.
+            const uint32_t idesc_kn = umma_idesc_bf16(128, 64, 0, 1);
             for (int b = 0; b < n_blocks; ++b) {
                 const int j = b / nt, i = b - j * nt;
-                const int ksteps = width(i) >> 4, k_lo = min(ksteps, 4);
+                const int ksteps = width(i) >> 4;
                 const uint8_t* do_i = sm_do + i * kBlkBytes;
                 const uint8_t* q_i = sm_q + i * kBlkBytes;
-                // columns [0, 64) of P^T / dS^T are stored: first half of dV_j += P^T dO_i and dK_j += dS^T Q_i
+                const uint8_t* dst_b = sm_dst + (b & 1) * 2 * kBlkBytes;
+                bool fresh = (i == 0);  // first K-step of a key tile overwrites the accumulators
+                // K-step ks = 16 queries: columns [16 ks, +16) of the block; the warps with phase = ks >> 2 store them
+                auto grad_step = [&](int ks) {
+                    if (ks >= ksteps) return;
+                    const uint64_t db_do = umma_smem_desc_sw128(smem_u32(do_i + ks * 2048));
+                    const uint64_t db_q = umma_smem_desc_sw128(smem_u32(q_i + ks * 2048));
+                    const uint64_t da_ds = umma_smem_desc_sw128(smem_u32(dst_b + (ks >> 2) * kBlkBytes + (ks & 3) * 32));
+                    umma_f16_ts(tmem + kColDV, tmem + kColST + 64 * (ks >> 2) + 8 * (ks & 3), db_do, idesc_kn, !fresh);
+                    umma_f16(tmem + kColDK, da_ds, db_q, idesc_kn, !fresh);
+                    fresh = false;
+                };
                 mbar_wait(&bars[3], b & 1);
                 tc_fence_after();
-                mma_blocks_x_cols(tmem + kColDV, sm_pt, do_i, k_lo, i != 0);
-                mma_blocks_x_cols(tmem + kColDK, sm_dst, q_i, k_lo, i != 0);
-                // all columns stored (and S^T / dP^T consumed)
+                grad_step(0), grad_step(4), grad_step(1), grad_step(5);
+                // everything stored (and S^T / dP^T consumed)
                 mbar_wait(&bars[4], b & 1);
                 PCG_TRACE(16 + b);
                 tc_fence_after();
-                if (ksteps > 4) {
-                    mma_blocks_x_cols(tmem + kColDV, sm_pt + kBlkBytes, do_i + 4 * 2048, ksteps - 4, true);
-                    mma_blocks_x_cols(tmem + kColDK, sm_dst + kBlkBytes, q_i + 4 * 2048, ksteps - 4, true);
-                }
-                mma_rows_t_x_cols(tmem + kColDQ + 64 * i, sm_dst, sm_k + j * kBlkBytes, 8, j != 0);  // dQ_i += dS K_j
-                if (i == nt - 1) umma_commit(&bars[5]);  // dV_j, dK_j complete (and dQ after the last tile)
+                grad_step(2), grad_step(6), grad_step(3), grad_step(7);
+                if (i == nt - 1) umma_commit(&bars[5]);  // dV_j, dK_j complete
                 if (b + 1 < n_blocks) {
                     const int j2 = (b + 1) / nt, i2 = (b + 1) - j2 * nt;
                     mma_tile_x_rows(tmem + kColST, sm_k + j2 * kBlkBytes, sm_q + i2 * kBlkBytes, width(i2));
                     mma_tile_x_rows(tmem + kColDPT, sm_v + j2 * kBlkBytes, sm_do + i2 * kBlkBytes, width(i2));
                     umma_commit(&bars[2]);
                 }
+                mma_rows_t_x_cols(tmem + kColDQ + 64 * i, dst_b, sm_k + j * kBlkBytes, 8, j != 0);  // dQ_i += dS K_j
             }
+            umma_commit(&bars[7]);
         }
     } else if (warp >= 9) {
         // edge token x = nv: column x (key x against every query) and row x (query x against every key) of the
@@ -1032,37 +1048,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                 mbar_wait(&bars[2], b & 1);
                 tc_fence_after();
                 if (warp == 0) PCG_TRACE(4 + 2 * b);
-                // this warp's columns: [32 phase, +32) of the first 64-column block, then of the second; 16 at a
-                // time with the next TMEM load in flight behind the arithmetic
-                const int c0 = phase * 32, c1 = 64 + phase * 32;
+                // this warp's columns: the 64-column block `phase`, 16 at a time with the next TMEM load in flight behind
+                // the arithmetic.  P^T goes back into tensor memory over S^T columns this warp has already read
+                // (packed: 8 columns per 16 queries), dS^T into this block's shared-memory buffer.
+                const int cb = 64 * phase;
+                uint8_t* dst_blk = sm_dst + (b & 1) * 2 * kBlkBytes + phase * kBlkBytes;
                 uint32_t sa[16], da[16], sb[16], db[16];
-                Cols16 o;
-                if (c0 < width) tmem_ld<16>(trow + kColST + c0, sa), tmem_ld<16>(trow + kColDPT + c0, da);
+                auto finish = [&](const uint32_t(&sv)[16], const uint32_t(&dv)[16], int g) {
+                    const Cols16 o = bwd_cols16(sv, dv, l2 + cb + 16 * g, dl + cb + 16 * g, row_ok);
+                    bwd_store_ds(o, dst_blk, r, 2 * g);
+                    const uint32_t pk[8] = {o.p[0].x, o.p[0].y, o.p[0].z, o.p[0].w, o.p[1].x, o.p[1].y, o.p[1].z, o.p[1].w};
+                    tmem_st<8>(trow + kColST + cb + 8 * g, pk);
+                };
+                if (cb < width) tmem_ld<16>(trow + kColST + cb, sa), tmem_ld<16>(trow + kColDPT + cb, da);
                 tmem_wait_ld();
-                if (c0 + 16 < width) tmem_ld<16>(trow + kColST + c0 + 16, sb), tmem_ld<16>(trow + kColDPT + c0 + 16, db);
-                if (c0 < width) {
-                    o = bwd_cols16(sa, da, l2 + c0, dl + c0, row_ok);
-                    bwd_store16(o, sm_pt, sm_dst, r, c0 >> 3);
-                }
+                if (cb + 16 < width) tmem_ld<16>(trow + kColST + cb + 16, sb), tmem_ld<16>(trow + kColDPT + cb + 16, db);
+                if (cb < width) finish(sa, da, 0);
                 tmem_wait_ld();
-                if (c1 < width) tmem_ld<16>(trow + kColST + c1, sa), tmem_ld<16>(trow + kColDPT + c1, da);
-                if (c0 + 16 < width) {
-                    o = bwd_cols16(sb, db, l2 + c0 + 16, dl + c0 + 16, row_ok);
-                    bwd_store16(o, sm_pt, sm_dst, r, (c0 + 16) >> 3);
-                }
-                tmem_wait_ld();
-                if (c1 + 16 < width) tmem_ld<16>(trow + kColST + c1 + 16, sb), tmem_ld<16>(trow + kColDPT + c1 + 16, db);
-                if (c1 < width) o = bwd_cols16(sa, da, l2 + c1, dl + c1, row_ok);
-                // the first block's stores have drained behind the arithmetic above: this fence is cheap
+                if (cb + 32 < width) tmem_ld<16>(trow + kColST + cb + 32, sa), tmem_ld<16>(trow + kColDPT + cb + 32, da);
+                if (cb + 16 < width) finish(sb, db, 1);
+                tmem_wait_st();
                 fence_proxy_async();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[3]);
-                if (c1 < width) bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 - 64) >> 3);
                 tmem_wait_ld();
-                if (c1 + 16 < width) {
-                    o = bwd_cols16(sb, db, l2 + c1 + 16, dl + c1 + 16, row_ok);
-                    bwd_store16(o, sm_pt + kBlkBytes, sm_dst + kBlkBytes, r, (c1 + 16 - 64) >> 3);
-                }
+                if (cb + 48 < width) tmem_ld<16>(trow + kColST + cb + 48, sb), tmem_ld<16>(trow + kColDPT + cb + 48, db);
+                if (cb + 32 < width) finish(sa, da, 2);
+                tmem_wait_ld();
+                if (cb + 48 < width) finish(sb, db, 3);
+                tmem_wait_st();
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
@@ -1086,6 +1101,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             tc_fence_before();
         }
         // dQ_i (+ the edge key's contribution)
+        mbar_wait(&bars[7], 0);
+        tc_fence_after();
         for (int i = 0; i < nt; ++i)
             bwd_epilogue(trow + kColDQ + 64 * i + phase * 32, dscol[i * 128 + r], kx + phase * 32, stage, lane, gd,
                          static_cast<size_t>(3) * D, i * 128 + quarter * 32, nv);
