@@ -816,9 +816,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     float* dox = qx + 192;
     float* scal = qx + 256;  // [0] p_xx, [1] ds_xx, [2] lse2_x, [3] delta_x
     // mbarriers: 0 first block's operands landed, 1 all operands landed, 2 S^T / dP^T ready, 3 / 4 first / second half
-    // of every warp's P^T and dS^T columns stored, 5 dV_j / dK_j complete, 6 edge vectors ready, 7 every dQ MMA retired
+    // of every warp's P^T and dS^T columns stored, 5 dV_j / dK_j complete, 6 edge row vectors (prow, dsrow) ready,
+    // 7 every dQ MMA retired, 8 edge column vectors (pcol, dscol) ready
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kBwdOffBar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, n = blockIdx.y;
@@ -866,6 +867,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             mbar_init(&bars[5], 1);
             mbar_init(&bars[6], 3);
             mbar_init(&bars[7], 1);
+            mbar_init(&bars[8], 3);
             fence_barrier_init();
             mbar_arrive_expect_tx(&bars[0], 4 * kBlkBytes);
             tma_load_3d(&map_qkv, &bars[0], sm_k, D + h * kHd, 0, n, kEvictFirst);
@@ -978,22 +980,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             umma_commit(&bars[7]);
         }
     } else if (warp >= 9) {
-        // edge token x = nv: column x (key x against every query) and row x (query x against every key) of the
-        // score matrix, one dot product per token and side, then the three matrix-vector products for row x of
-        // dV, dK and dQ.  Runs beside the tensor-core pipeline; the epilogues pick the vectors up at the end.
-        named_bar_sync(1, kBwdThreads - 32);  // delta[] is complete
+        // edge token x = nv: row x (query x against every key) and column x (key x against every query) of the score
+        // matrix, one dot product per token and side, then the three matrix-vector products for row x of dV, dK and
+        // dQ.  Runs beside the tensor-core pipeline.  Row x comes first: the first key tile's epilogue needs it and it
+        // does not depend on delta[]; column x follows once delta[] is complete and is needed by the dQ epilogue.
         mbar_wait(&bars[0], 0);
         mbar_wait(&bars[1], 0);
         const float lse2_x = scal[2], delta_x = scal[3];
         for (int t = (warp - 9) * 32 + lane; t < 256; t += 96) {
-            float pc = 0.f, dsc = 0.f, pr = 0.f, dsr = 0.f;
+            float pr = 0.f, dsr = 0.f;
             if (t < nv) {
-                pc = exp2f(fmaf(row_dot(sm_q, t, kx), kLog2e, -lse2[t]));
-                dsc = pc * (row_dot(sm_do, t, vx) - delta[t]);
                 pr = exp2f(fmaf(row_dot(sm_k, t, qx), kLog2e, -lse2_x));
                 dsr = pr * (row_dot(sm_v, t, dox) - delta_x);
             }
-            pcol[t] = pc, dscol[t] = dsc, prow[t] = pr, dsrow[t] = dsr;
+            prow[t] = pr, dsrow[t] = dsr;
         }
         if (warp == 9 && lane == 0) {
             float sxx = 0.f, dpxx = 0.f;
@@ -1004,7 +1004,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[6]);
+        named_bar_sync(1, kBwdThreads - 32);  // delta[] is complete
+        for (int t = (warp - 9) * 32 + lane; t < 256; t += 96) {
+            float pc = 0.f, dsc = 0.f;
+            if (t < nv) {
+                pc = exp2f(fmaf(row_dot(sm_q, t, kx), kLog2e, -lse2[t]));
+                dsc = pc * (row_dot(sm_do, t, vx) - delta[t]);
+            }
+            pcol[t] = pc, dscol[t] = dsc;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[8]);
         mbar_wait(&bars[6], 0);
+        mbar_wait(&bars[8], 0);
         if (warp == 9) PCG_TRACE(2);
         bf16* gx = p.d_qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd;
         if (warp == 9) edge_gemv(pcol, sm_do, nv, scal[0], dox, gx + 2 * D, 1.0f, lane);  // dV_x
@@ -1101,6 +1113,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             tc_fence_before();
         }
         // dQ_i (+ the edge key's contribution)
+        mbar_wait(&bars[8], 0);
         mbar_wait(&bars[7], 0);
         tc_fence_after();
         for (int i = 0; i < nt; ++i)
