@@ -197,6 +197,39 @@ def test_attention(cuda_device, n, t, heads, tc):
         check_close(d_qkv[:, sl], ref.grad[:, sl], 1.5e-2, f"attention {name} T={t} tc={tc}")
 
 
+def test_attention_random_shapes_repeated(cuda_device):
+    """Every tensor-core path (packed T <= 64, fused 66..257, streaming > 257) on seeded random shapes, each run twice
+    on fresh data: a race between the elementwise warps and the MMA pipe (P^T / dS^T buffers reused across blocks)
+    shows up as a run-to-run difference or as an error that the fixed shapes above happen to miss."""
+    rng = np.random.default_rng(7)
+    shapes = [(int(rng.integers(1, 5)), int(t), int(h)) for t, h in
+              zip(rng.integers(2, 700, size=14), rng.choice([2, 4, 6], size=14))]
+    shapes += [(6, 257, 16), (9, 197, 12), (2, 577, 4), (7, 50, 12)]
+    for n, t, heads in shapes:
+        d = heads * 64
+        for rep in range(2):
+            g = torch.Generator(device="cpu").manual_seed(1000 * t + 10 * heads + rep)
+            qkv = torch.randn(n * t, 3 * d, generator=g)
+            qkv[:, :d] *= 0.25
+            qkv = qkv.to(cuda_device, bf16)
+            d_out = torch.randn(n * t, d, generator=g).to(cuda_device, bf16)
+            out, lse = ops.attn_fwd(qkv, n, t, heads)
+            d_qkv = ops.attn_bwd(qkv, out, d_out, lse, n, t, heads)
+            out2, lse2 = ops.attn_fwd(qkv, n, t, heads)
+            d_qkv2 = ops.attn_bwd(qkv, out2, d_out, lse2, n, t, heads)
+            assert torch.equal(out, out2) and torch.equal(lse, lse2), f"forward not reproducible n={n} T={t} heads={heads}"
+            if t <= 257:  # the streaming backward reduces dQ with fp32 atomics: order-dependent in the last bits
+                assert torch.equal(d_qkv, d_qkv2), f"backward not reproducible n={n} T={t} heads={heads}"
+            ref = qkv.float().clone().requires_grad_()
+            o_ref, lse_ref = attn_reference(ref, n, t, heads)
+            o_ref.backward(d_out.float())
+            check_close(out, o_ref, 6e-3, f"fuzz fwd n={n} T={t} heads={heads}")
+            check_close(lse, lse_ref, 1e-3, f"fuzz lse n={n} T={t} heads={heads}")
+            for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+                check_close(d_qkv[:, sl], ref.grad[:, sl], 1.5e-2, f"fuzz {name} n={n} T={t} heads={heads}")
+                check_close(d_qkv2[:, sl], ref.grad[:, sl], 1.5e-2, f"fuzz {name} (2nd run) n={n} T={t} heads={heads}")
+
+
 # ------------------------------------------------------------------------------------------------ head
 def head_reference(x, ln_g, ln_b, proj, targets, tw, n, t, scale, normalize=True):
     d = x.shape[1]
