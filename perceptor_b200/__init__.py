@@ -3,7 +3,13 @@
     from perceptor_b200 import losses
     loss = losses.CLIP("ViT-L-14", n_cutouts=128).add_encodings_(text_encodings)
     loss(images).backward()          # images.grad: [B,3,H,W]
-"""
-from . import cutouts, losses, models, resize_tables, vit  # noqa: F401
 
-__all__ = ["losses", "models", "cutouts", "resize_tables", "vit"]
+Beside the hot path (losses, models, cutouts, resize_tables, vit, guidance, native) the package carries the callers'
+glue it was widened into: velocity_diffusion (Predictions, schedule_ts, guided_step), transforms
+(clamp_with_grad), utils (gradient_checkpoint), text (CLIP tokenizer + text tower) and checkpoints (OpenAI /
+open_clip / Hugging Face state-dict ingestion).
+"""
+from . import checkpoints, cutouts, losses, models, resize_tables, text, transforms, utils, velocity_diffusion, vit  # noqa: F401
+
+__all__ = ["losses", "models", "cutouts", "resize_tables", "vit", "velocity_diffusion", "transforms", "utils", "text",
+           "checkpoints"]
