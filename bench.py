@@ -44,6 +44,28 @@ NCU_GEMM_TRAFFIC_BYTES = {"vit_l14_224_128cut_512px": 363.7e6}
 METRIC = "CLIP-guidance cutouts/sec (loss + image grad), ViT-L/14, at 1/2/4/8 B200"
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner at communicator
+    creation), so file descriptor 1 is pointed at stderr for the run and the result goes out through a saved copy."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -173,7 +195,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": value, "unit": "cutouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -320,7 +342,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         line["cpu_baseline"] = {"value": cpu_value, "unit": "cutouts/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{args.cpu_sample} cutouts/step of the same workload, {cpu_done} timed steps "
                                           f"(median {cpu_med:.2f} s), fp32 torch CPU oracle, {os.cpu_count()} host cpus"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -339,6 +361,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
