@@ -62,5 +62,16 @@ def main():
     print("text goldens written", enc.shape)
 
 
+
+
+def textoff_fixture():
+    """the reference's "text off" target vectors for the ViT towers of the hot path, copied as a
+    small fixture so that the GPU box (which has no /root/reference) can use a realistic target."""
+    d = json.loads((REF / "losses" / "clip" / "vectors" / "textoff.json").read_text())
+    np.savez_compressed(OUT / "textoff_vit.npz", **{k.replace("-", "_"): np.asarray(d[k], dtype=np.float32)
+                                                     for k in ("ViT-B-32", "ViT-B-16")})
+
+
 if __name__ == "__main__":
     main()
+    textoff_fixture()

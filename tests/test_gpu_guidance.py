@@ -145,6 +145,34 @@ def test_exact_gelu_towers_match_oracle(cuda_device):
     assert losses.OpenCLIP("ViT-L-14", "openai").model.act == native.ACT_QUICKGELU
 
 
+def test_text_off_target_from_the_reference(cuda_device, tmp_path):
+    """the reference's own "text off" vector for ViT-B-32 (losses/clip/vectors/textoff.json, kept
+    as tests/golden/textoff_vit.npz) as a realistic, negatively weighted target through add_text_off_, against the
+    oracle loss on the same cutouts."""
+    import json
+    from pathlib import Path
+
+    vec = np.load(Path(__file__).parent / "golden" / "textoff_vit.npz")["ViT_B_32"]
+    stub = tmp_path / "textoff.json"
+    stub.write_text(json.dumps({"ViT-B-32": vec.tolist()}))
+    loss = losses.CLIP("ViT-B-32", n_cutouts=3, min_size=64, seed=2)
+    g = torch.Generator().manual_seed(0)
+    loss.add_encodings_(torch.randn(1, 512, generator=g)).add_text_off_(weight=[-0.3], path=str(stub))
+    assert loss.encodings.shape == (2, 512) and loss.weights.tolist() == pytest.approx([1.0, -0.3])
+    images = torch.rand(1, 3, 128, 160, generator=g)
+    x = images.to(cuda_device).requires_grad_()
+    value = loss(x)
+    value.backward()
+    ref_img = images.clone().requires_grad_()
+    sd = {k: v.detach().cpu() for k, v in loss.model.state_dict_openai().items()}
+    s = loss.model.shape
+    ref = guidance_oracle.guidance_loss(ref_img, loss.last_cutouts.tolist(), sd, s.image_size, s.patch, s.layers, s.heads,
+                                        loss.encodings.detach().cpu(), loss.weights.detach().cpu(), 1.0)
+    ref.backward()
+    assert abs(float(value.detach()) - float(ref.detach())) <= LOSS_RTOL * abs(float(ref.detach()))
+    assert cosine(x.grad.cpu(), ref_img.grad) >= GRAD_COS
+
+
 def test_whole_image_mode_is_reference_behaviour(cuda_device):
     """n_cutouts=None: every whole (non-square) image is resized, exactly what the reference does."""
     g = torch.Generator().manual_seed(2)
