@@ -31,6 +31,7 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -489,6 +490,339 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const FwdParams 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) PCG_TRACE(10);
+    if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward, persistent (the production kernel for 66 <= T <= 257)
+// ---------------------------------------------------------------------------------------------------------
+// Same arithmetic and the same tensor-memory plan as attn_fwd_tc_kernel, but a CTA no longer dies with its tile: the
+// grid is 2 CTAs per SM and every CTA walks the work items (cutout, head, query tile) w = blockIdx.x + it * gridDim.x.
+// What the one-shot kernel pays per tile -- barrier setup and the tensor-memory allocation (~1500 clk), the TMA round
+// trip for Q, K and V (~1500 clk) and the drain of its last warp (~1000 clk) of a ~14000 clk lifetime -- is paid once
+// per CTA, and the operands of item it + 1 are in flight while item it computes:
+//   * Q is double buffered (slot it & 1; the slot also stages the O tile of its item for the coalesced stores),
+//   * K is reloaded as soon as S(it) = Q K^T has retired and the edge warp has read it, V as soon as O(it) = P V has,
+//   * S(it + 1) is issued the moment the softmax warps have pulled O(it) out of tensor memory, so it runs under
+//     their global stores.
+// One thread (warp 4, lane 0) issues both the TMA loads and the MMAs in a fixed order per item:
+//   S(it) -> loads Q, K of it + 1 -> P V (it) -> load V of it + 1.
+// Every mbarrier completes exactly once per item (or once per use of a Q slot) and no waiter can fall a phase behind:
+// see the comments at the waits.
+constexpr int kFwd2OffQ = 4 * kBlkBytes;                 // two Q slots
+constexpr int kFwd2OffX = 6 * kBlkBytes;                 // 2 x {k_x[64], v_x[64], q_x[64]} floats, then p_x[256]
+constexpr int kFwd2OffBar = kFwd2OffX + 2 * 768 + 1024;  // 16 mbarriers + tmem slot
+constexpr int kFwd2SmemBytes = kFwd2OffBar + 16 * 8 + 64 + 1024;
+enum {
+    kB2FullQK = 0,    // [2] Q slot + K landed                      (TMA)
+    kB2FullV = 2,     // V landed                                   (TMA)
+    kB2SReady = 3,    // S = Q K^T retired                          (tcgen05.commit)
+    kB2PHi = 4,       // P(keys >= 128) stored by the 4 softmax warps
+    kB2PLo = 5,       // P(keys < 128) stored
+    kB2OReady = 6,    // O = P V retired                            (tcgen05.commit)
+    kB2TmemFree = 7,  // the 4 softmax warps have read O out of tensor memory
+    kB2Done = 8,      // [2] the 4 softmax warps are done with Q slot / edge vectors of their item
+    kB2XReady = 10,   // [2] edge-token vectors of the item written (edge warp)
+    kB2EdgeK = 12,    // edge warp done reading K
+    kB2EdgeV = 13,    // edge warp done reading V
+    kB2Count = 14
+};
+
+struct Fwd2Params {
+    int T, heads;
+    int nv, nk;
+    int tiles;  // query tiles per (cutout, head)
+    int items;  // n * heads * tiles
+    const bf16* qkv;
+    bf16* out;
+    float* lse;
+    long long* trace;    // optional [ctas][32] clock64 stamps of the CTA's second item
+    int stagger_cycles;  // every second CTA to arrive on an SM starts this much later (anti-phase, see above)
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2Params p) {
+    grid_dep_launch();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sm_k = sm;
+    uint8_t* sm_v = sm + kFwdOffV;
+    uint8_t* sm_q0 = sm + kFwd2OffQ;
+    float* xvec = reinterpret_cast<float*>(sm + kFwd2OffX);  // slot s: k_x = xvec + 192 s, v_x = + 64, q_x = + 128
+    float* pbuf = xvec + 384;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kFwd2OffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = p.heads * kHd, nv = p.nv, nk = p.nk;
+    const int nblk = (nk + 127) >> 7;
+    const int G = gridDim.x;
+    const int n_my = (p.items - static_cast<int>(blockIdx.x) + G - 1) / G;
+    const size_t cta_id = blockIdx.x;
+    // item it of this CTA -> (cutout, head, first query row)
+    auto decode = [&](int it, int& n, int& h, int& q0) {
+        const int w = static_cast<int>(blockIdx.x) + it * G;
+        const int tile = w % p.tiles, nh = w / p.tiles;
+        q0 = tile * 128;
+        h = nh % p.heads;
+        n = nh / p.heads;
+    };
+    auto load_qk = [&](int it) {
+        int n, h, q0;
+        decode(it, n, h, q0);
+        uint64_t* bar = &bars[kB2FullQK + (it & 1)];
+        mbar_arrive_expect_tx(bar, (nblk + 1) * kBlkBytes);
+        tma_load_3d(&map_qkv, bar, sm_q0 + (it & 1) * kBlkBytes, h * kHd, q0, n, kEvictFirst);
+        for (int i = 0; i < nblk; ++i)
+            tma_load_3d(&map_qkv, bar, sm_k + i * kBlkBytes, D + h * kHd, i * 128, n, kEvictNormal);
+    };
+    auto load_v = [&](int it) {
+        int n, h, q0;
+        decode(it, n, h, q0);
+        mbar_arrive_expect_tx(&bars[kB2FullV], nblk * kBlkBytes);
+        for (int i = 0; i < nblk; ++i)
+            tma_load_3d(&map_qkv, &bars[kB2FullV], sm_v + i * kBlkBytes, 2 * D + h * kHd, i * 128, n, kEvictNormal);
+    };
+    // the edge token's q, k, v rows of an item, two bf16 per lane (edge warp)
+    auto load_x = [&](int it, uint32_t& xq, uint32_t& xk, uint32_t& xv) {
+        int n, h, q0;
+        decode(it, n, h, q0);
+        const bf16* xrow_g = p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd + 2 * lane;
+        xq = *reinterpret_cast<const uint32_t*>(xrow_g);
+        xk = *reinterpret_cast<const uint32_t*>(xrow_g + D);
+        xv = *reinterpret_cast<const uint32_t*>(xrow_g + 2 * D);
+    };
+
+    uint32_t xq = 0, xk = 0, xv = 0;
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(&bars[kB2FullQK], 1);
+            mbar_init(&bars[kB2FullQK + 1], 1);
+            mbar_init(&bars[kB2FullV], 1);
+            mbar_init(&bars[kB2SReady], 1);
+            mbar_init(&bars[kB2PHi], 4);
+            mbar_init(&bars[kB2PLo], 4);
+            mbar_init(&bars[kB2OReady], 1);
+            mbar_init(&bars[kB2TmemFree], 4);
+            mbar_init(&bars[kB2Done], 4);
+            mbar_init(&bars[kB2Done + 1], 4);
+            mbar_init(&bars[kB2XReady], 1);
+            mbar_init(&bars[kB2XReady + 1], 1);
+            mbar_init(&bars[kB2EdgeK], 1);
+            mbar_init(&bars[kB2EdgeV], 1);
+            fence_barrier_init();
+            if (p.stagger_cycles > 0) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                if (atomicAdd(&g_fwd_sm_arrivals[smid & 1023], 1u) & 1u) {
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < p.stagger_cycles) {
+                    }
+                }
+            }
+            load_qk(0);
+            load_v(0);
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    } else if (warp == 5) {
+        load_x(0, xq, xk, xv);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+            const int ksteps = nk >> 4;
+#pragma unroll 1
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it & 1;
+                // ---- S(it) = Q K^T, as soon as the operands are in and O(it - 1) has left tensor memory
+                mbar_wait(&bars[kB2FullQK + s], (it >> 1) & 1);
+                if (it > 0) mbar_wait(&bars[kB2TmemFree], (it - 1) & 1);
+                tc_fence_after();
+                mma_tile_x_rows(tmem, sm_q0 + s * kBlkBytes, sm_k, nk);
+                umma_commit(&bars[kB2SReady]);
+                // ---- Q, K of item it + 1: the other Q slot is free once the epilogue of item it - 1 has drained it,
+                // K once S(it) has retired and the edge warp has taken its dot products
+                if (it + 1 < n_my) {
+                    if (it >= 1) mbar_wait(&bars[kB2Done + (s ^ 1)], ((it - 1) >> 1) & 1);
+                    mbar_wait(&bars[kB2SReady], it & 1);
+                    mbar_wait(&bars[kB2EdgeK], it & 1);
+                    load_qk(it + 1);
+                }
+                // ---- O(it) = P V with A = P from tensor memory, keys >= 128 first
+                mbar_wait(&bars[kB2FullV], it & 1);
+                if (ksteps > 8) {
+                    mbar_wait(&bars[kB2PHi], it & 1);
+                    tc_fence_after();
+                    for (int ks = 8; ks < ksteps; ++ks)
+                        umma_f16_ts(tmem + kFwdColO, tmem + kFwdColPHi + (ks - 8) * 8,
+                                    umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)), idesc_pv, ks != 8);
+                }
+                mbar_wait(&bars[kB2PLo], it & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < min(ksteps, 8); ++ks)
+                    umma_f16_ts(tmem + kFwdColO, tmem + ks * 8, umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)),
+                                idesc_pv, ksteps > 8 || ks != 0);
+                umma_commit(&bars[kB2OReady]);
+                // ---- V of item it + 1 once P V has retired and the edge warp has finished its row
+                if (it + 1 < n_my) {
+                    mbar_wait(&bars[kB2OReady], it & 1);
+                    mbar_wait(&bars[kB2EdgeV], it & 1);
+                    load_v(it + 1);
+                }
+            }
+        }
+    } else if (warp < 4) {
+        const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
+        const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const int nk32 = (nk + 31) & ~31;
+#pragma unroll 1
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it & 1;
+            int n, h, q0;
+            decode(it, n, h, q0);
+            uint8_t* sm_q = sm_q0 + s * kBlkBytes;
+            const float* kx = xvec + 192 * s;
+            const float* vx = kx + 64;
+            const bool tr = (it == 1) && warp == 0 && p.trace != nullptr && lane == 0;
+            if (tr) p.trace[cta_id * 32 + 0] = clock64();
+            mbar_wait(&bars[kB2XReady + s], (it >> 1) & 1);
+            mbar_wait(&bars[kB2FullQK + s], (it >> 1) & 1);
+            const float sx = row_dot(sm_q, r, kx);  // score against the edge key, while the MMA runs
+            mbar_wait(&bars[kB2SReady], it & 1);
+            tc_fence_after();
+            if (tr) p.trace[cta_id * 32 + 4] = clock64();
+            const float mx = fwd_row_max(trow, nk32, nv, sx);
+            const float mb = mx * kLog2e;
+            if (tr) p.trace[cta_id * 32 + 5] = clock64();
+            float sum = 0.f;
+            if (nk32 > 128) sum = fwd_row_exp(trow, 128, nk32, kFwdColPHi, nv, mb, sum);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2PHi]);
+            sum = fwd_row_exp(trow, 0, min(nk32, 128), 0, nv, mb, sum);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2PLo]);
+            if (tr) p.trace[cta_id * 32 + 6] = clock64();
+            const float px = exp2f(fmaf(sx, kLog2e, -mb));
+            sum += px;
+            if (q0 + r < nv) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + q0 + r] = mx + logf(sum);
+            const float inv = 1.0f / sum;
+            mbar_wait(&bars[kB2OReady], it & 1);
+            tc_fence_after();
+            if (tr) p.trace[cta_id * 32 + 7] = clock64();
+            uint32_t v[64];
+            tmem_ld_32x32(trow + kFwdColO, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+            tmem_ld_32x32(trow + kFwdColO + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
+            tmem_wait_ld();
+            // O is in registers: tensor memory may take S of the next item
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2TmemFree]);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 xa = *reinterpret_cast<const float4*>(vx + g * 8);
+                const float4 xb = *reinterpret_cast<const float4*>(vx + g * 8 + 4);
+                const uint4 o = make_uint4(pack_bf16(fmaf(px, xa.x, __uint_as_float(v[8 * g])) * inv,
+                                                     fmaf(px, xa.y, __uint_as_float(v[8 * g + 1])) * inv),
+                                           pack_bf16(fmaf(px, xa.z, __uint_as_float(v[8 * g + 2])) * inv,
+                                                     fmaf(px, xa.w, __uint_as_float(v[8 * g + 3])) * inv),
+                                           pack_bf16(fmaf(px, xb.x, __uint_as_float(v[8 * g + 4])) * inv,
+                                                     fmaf(px, xb.y, __uint_as_float(v[8 * g + 5])) * inv),
+                                           pack_bf16(fmaf(px, xb.z, __uint_as_float(v[8 * g + 6])) * inv,
+                                                     fmaf(px, xb.w, __uint_as_float(v[8 * g + 7])) * inv));
+                *reinterpret_cast<uint4*>(sm_q + row_chunk(r, g)) = o;
+            }
+            __syncwarp();
+            bf16* gout = p.out + static_cast<size_t>(n) * p.T * D + h * kHd;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = warp * 32 + i * 4 + (lane >> 3), ch = lane & 7;
+                if (q0 + row < nv)
+                    *reinterpret_cast<uint4*>(gout + static_cast<size_t>(q0 + row) * D + ch * 8) =
+                        *reinterpret_cast<const uint4*>(sm_q + row_chunk(row, ch));
+            }
+            // this warp's rows of the Q slot (written above with ordinary stores) go back to the TMA unit
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2Done + s]);
+            if (tr) p.trace[cta_id * 32 + 8] = clock64();
+        }
+    } else {
+        // edge warp: the edge token's vectors for everyone, and (for the CTA of the last tile) query row x on the CUDA
+        // cores.  Its loads of item it + 1 are issued before the work of item it.
+#pragma unroll 1
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it & 1;
+            int n, h, q0;
+            decode(it, n, h, q0);
+            const bool has_edge_row = (q0 + 128 >= nv);
+            float* kx = xvec + 192 * s;
+            float* vx = kx + 64;
+            float* qx = kx + 128;
+            // slot s was last read by the softmax warps of item it - 2
+            if (it >= 2) mbar_wait(&bars[kB2Done + s], ((it - 2) >> 1) & 1);
+            qx[2 * lane] = bf_lo(xq), qx[2 * lane + 1] = bf_hi(xq);
+            kx[2 * lane] = bf_lo(xk), kx[2 * lane + 1] = bf_hi(xk);
+            vx[2 * lane] = bf_lo(xv), vx[2 * lane + 1] = bf_hi(xv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2XReady + s]);
+            if (it + 1 < n_my) load_x(it + 1, xq, xk, xv);
+            mbar_wait(&bars[kB2FullQK + s], (it >> 1) & 1);
+            float sc[8];
+            float sxx = 0.f;
+            if (has_edge_row) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = lane + 32 * jj;
+                    sc[jj] = (j < nv) ? row_dot(sm_k, j, qx) : -INFINITY;
+                }
+#pragma unroll
+                for (int d = 0; d < 64; ++d) sxx = fmaf(qx[d], kx[d], sxx);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2EdgeK]);
+            if (has_edge_row) {
+                float mx = sxx;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) mx = fmaxf(mx, sc[jj]);
+                mx = warp_max(mx);
+                const float mb = mx * kLog2e;
+                float part = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    sc[jj] = exp2f(fmaf(sc[jj], kLog2e, -mb));
+                    part += sc[jj];
+                    pbuf[lane + 32 * jj] = sc[jj];
+                }
+                const float exx = exp2f(fmaf(sxx, kLog2e, -mb));
+                const float sum = warp_sum(part) + exx;
+                __syncwarp();
+                mbar_wait(&bars[kB2FullV], it & 1);
+                edge_gemv(pbuf, sm_v, nv, exx, vx, p.out + (static_cast<size_t>(n) * p.T + nv) * D + h * kHd, 1.0f / sum,
+                          lane);
+                if (lane == 0) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + nv] = mx + logf(sum);
+            } else {
+                // no row to compute, but still keep step with the V loads: the arrival below must not run a phase
+                // ahead of the issuing thread's wait for it (V of item it + 1 is only requested after that wait)
+                mbar_wait(&bars[kB2FullV], it & 1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2EdgeV]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
     if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
@@ -1734,6 +2068,12 @@ int g_fwd_stagger = []() {
     return e != nullptr ? atoi(e) : 5000;
 }();
 
+// PCG_ATTN_PERSIST=0 sends 66 <= T <= 257 back to the one-tile-per-CTA kernels (kept for A/B measurements and tests)
+bool g_fwd_persist = []() {
+    const char* e = getenv("PCG_ATTN_PERSIST");
+    return !(e != nullptr && e[0] == '0');
+}();
+
 bool g_force_legacy = []() {
     const char* e = getenv("PCG_ATTN_LEGACY");
     return e != nullptr && e[0] == '1';
@@ -1746,6 +2086,11 @@ using namespace pcg;
 
 extern "C" int pcg_attn_set_legacy(int on) {  // test hook: force the mma.sync kernels for every row
     g_force_legacy = on != 0;
+    return 0;
+}
+
+extern "C" int pcg_attn_set_persist(int on) {  // test / benchmark hook: persistent (1) or one-shot (0) tcgen05 kernels
+    g_fwd_persist = on != 0;
     return 0;
 }
 
@@ -1789,12 +2134,20 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
         PCG_LAUNCH_CHECK("attn_fwd_flash_kernel");
         return 0;
     }
-    static bool configured = false;
-    if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
-        configured = true;
-    }
     const int nv = T - 1;
+    if (g_fwd_persist) {
+        PCG_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2SmemBytes));
+        const int tiles = (nv + 127) / 128;
+        const long long items = static_cast<long long>(n) * heads * tiles;
+        PCG_CHECK_ARG(items < (1ll << 30), "pcg_attn_fwd: too many (cutout, head, tile) items");
+        Fwd2Params p2{T, heads, nv, (nv + 15) & ~15, tiles, static_cast<int>(items), static_cast<const bf16*>(qkv),
+                      static_cast<bf16*>(out), lse, g_trace, g_fwd_stagger};
+        const int grid = static_cast<int>(std::min<long long>(items, 2ll * sm_count()));
+        attn_fwd_persist_kernel<<<grid, kFwdThreads, kFwd2SmemBytes, s>>>(map, p2);
+        PCG_LAUNCH_CHECK("attn_fwd_persist_kernel");
+        return 0;
+    }
+    PCG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
     FwdParams p{T, heads, nv, (nv + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
                 g_trace, 2 * sm_count(), g_fwd_stagger};
     attn_fwd_tc_kernel<<<dim3((nv + 127) / 128, heads, n), kFwdThreads, kFwdSmemBytes, s>>>(map, p);

@@ -175,6 +175,25 @@ def attn_reference(qkv, n, t, heads):
                                        (3, 50, 4), (1, 33, 4), (1, 2, 2), (2, 64, 6), (1, 50, 1), (2, 16, 2)])
 @pytest.mark.parametrize("tc", [0, 1])
 def test_attention(cuda_device, n, t, heads, tc):
+    run_attention_case(cuda_device, n, t, heads, tc)
+
+
+@pytest.mark.parametrize("n,t,heads", [(40, 257, 16), (33, 197, 12), (150, 130, 2), (19, 257, 16), (75, 66, 4),
+                                       (3, 257, 16), (2, 192, 3)])
+@pytest.mark.parametrize("persist", [0, 1])
+def test_attention_persistent_ctas(cuda_device, n, t, heads, persist):
+    """66 <= T <= 257 with more (cutout, head, tile) items than resident CTAs (2 per SM): every CTA of the persistent
+    forward walks several items, so the double-buffered Q slots, the K / V reloads and every barrier phase are
+    exercised (40 x 16 x 2 = 1280 items = 4-5 per CTA; 150 x 2 x 2 = 600 leaves some CTAs with two and some with
+    three; 19 x 16 x 2 = 608).  persist=0 runs the same shapes through the one-tile-per-CTA kernels."""
+    native.lib().pcg_attn_set_persist(persist)
+    try:
+        run_attention_case(cuda_device, n, t, heads, 1)
+    finally:
+        native.lib().pcg_attn_set_persist(1)
+
+
+def run_attention_case(cuda_device, n, t, heads, tc):
     """tc=1 routes T >= 66 through the tcgen05 kernels (the default; T > 257 streams the keys with an online
     softmax: 258 / 385 leave one key in the last chunk, 400 fifteen, 1025 fills eight chunks; T <= 64 with an even
     head count packs two heads per tile, an odd head count stays on mma.sync), tc=0 through the mma.sync kernels."""
@@ -204,7 +223,7 @@ def test_attention_random_shapes_repeated(cuda_device):
     rng = np.random.default_rng(7)
     shapes = [(int(rng.integers(1, 5)), int(t), int(h)) for t, h in
               zip(rng.integers(2, 700, size=14), rng.choice([2, 4, 6], size=14))]
-    shapes += [(6, 257, 16), (9, 197, 12), (2, 577, 4), (7, 50, 12)]
+    shapes += [(6, 257, 16), (9, 197, 12), (2, 577, 4), (7, 50, 12), (30, 257, 16)]
     for n, t, heads in shapes:
         d = heads * 64
         for rep in range(2):

@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from perceptor_b200 import ops  # noqa: E402
+from perceptor_b200 import native, ops  # noqa: E402
 
 
 def main():
@@ -15,7 +15,9 @@ def main():
     ap.add_argument("--t", type=int, default=257)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent CTAs")
     args = ap.parse_args()
+    native.lib().pcg_attn_set_persist(args.persist)
     dev = torch.device("cuda", 0)
     n, t, h = args.n, args.t, args.heads
     d = h * 64
@@ -41,7 +43,7 @@ def main():
         tb += e[1].elapsed_time(e[2])
     tf, tb = tf / args.iters, tb / args.iters
     fl = 4.0 * t * t * 64 * h * n
-    print(f"n={n} T={t} heads={h}: fwd {tf * 1e3:.1f} us ({fl / tf / 1e9:.0f} TF/s)  bwd {tb * 1e3:.1f} us ({2 * fl / tb / 1e9:.0f} TF/s algorithmic)")
+    print(f"persist={args.persist} n={n} T={t} heads={h}: fwd {tf * 1e3:.1f} us ({fl / tf / 1e9:.0f} TF/s)  bwd {tb * 1e3:.1f} us ({2 * fl / tb / 1e9:.0f} TF/s algorithmic)")
 
 
 if __name__ == "__main__":

@@ -10,6 +10,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perceptor_b200 import native, ops  # noqa: E402
 
+# persistent forward: stamps of each CTA's SECOND item (steady state), warp 0
+FWD2 = {0: "item start", 4: "S ready", 5: "max pass done", 6: "exp pass done", 7: "O ready", 8: "epilogue done"}
 FWD = {0: "start", 1: "setup done", 2: "K+Q landed", 3: "V landed", 4: "S ready (w0)", 5: "max pass done", 6: "exp pass done",
        7: "O ready", 8: "epilogue done", 9: "edge row done", 10: "all warps done"}
 BWD = {0: "start", 1: "first loads landed", 2: "edge vectors ready", 3: "edge gemv done", 4: "b0 S/dP ready", 5: "b0 alu done",
@@ -39,7 +41,9 @@ def main():
     ap.add_argument("--t", type=int, default=257)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--iters", type=int, default=8)
+    ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent CTAs")
     args = ap.parse_args()
+    native.lib().pcg_attn_set_persist(args.persist)
     dev = torch.device("cuda", 0)
     n, t, h = args.n, args.t, args.heads
     d = h * 64
@@ -70,7 +74,7 @@ def main():
     native.lib().pcg_attn_set_trace(trace.data_ptr())
     out, lse = ops.attn_fwd(qkv, n, t, h)
     torch.cuda.synchronize()
-    show(trace, FWD, "forward")
+    show(trace, FWD2 if args.persist else FWD, "forward (persistent, second item of each CTA)" if args.persist else "forward")
     trace.zero_()
     ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
     torch.cuda.synchronize()
