@@ -528,6 +528,57 @@ enum {
     kB2Count = 14
 };
 
+// ---- compact softmax helpers of the persistent forward.  The one-shot kernel above unrolls a full and a masked
+// variant of every 32-column step at every call site (~7k SASS instructions); run persistently, with two CTAs of six
+// warps at different points of a 90 KB loop body, that code missed the instruction caches all the time (ncu: a quarter
+// of all stall samples were no_instructions).  Here a partial chunk is patched to -inf in registers (32 selects, only
+// for the last chunk of a short sequence) and a single variant of the arithmetic follows.
+__device__ __noinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("pcg: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+// bounded wait with the slow path out of line (the inline one costs ~30 instructions per call site)
+__device__ __forceinline__ void mbar_wait_c(uint64_t* bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_spin(bar, parity);
+}
+__device__ __forceinline__ void mask_cols32(uint32_t (&v)[32], int c, int nv) {
+    if (c + 32 > nv) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (c + j >= nv) v[j] = 0xff800000u;  // -inf: drops out of the max, exp2 gives 0
+    }
+}
+__device__ __forceinline__ float max32(const uint32_t (&v)[32], float mx) {
+    float m0 = mx, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        m0 = fmaxf(m0, __uint_as_float(v[j]));
+        m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+    }
+    return fmaxf(m0, m1);
+}
+__device__ __forceinline__ float exp32(const uint32_t (&v)[32], float mb, uint32_t tdst, float sum) {
+    uint32_t pk[16];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float e0 = exp2f(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mb));
+        const float e1 = exp2f(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mb));
+        s0 += e0;
+        s1 += e1;
+        pk[j] = pack_bf16(e0, e1);
+    }
+    tmem_st<16>(tdst, pk);
+    return sum + (s0 + s1);
+}
+
+constexpr int kTraceItem = 5;  // the item of each CTA whose phases tools/attn_trace.py reports (steady state)
+
 struct Fwd2Params {
     int T, heads;
     int nv, nk;
@@ -563,10 +614,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
     // item it of this CTA -> (cutout, head, first query row)
     auto decode = [&](int it, int& n, int& h, int& q0) {
         const int w = static_cast<int>(blockIdx.x) + it * G;
-        const int tile = w % p.tiles, nh = w / p.tiles;
-        q0 = tile * 128;
-        h = nh % p.heads;
+        const int nh = (p.tiles == 2) ? (w >> 1) : w;  // tiles is 1 or 2
+        q0 = (p.tiles == 2) ? (w & 1) * 128 : 0;
         n = nh / p.heads;
+        h = nh - n * p.heads;
     };
     auto load_qk = [&](int it) {
         int n, h, q0;
@@ -634,6 +685,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[cta_id * 32 + 30] = clock64(), p.trace[cta_id * 32 + 29] = n_my;
 
     if (warp == 4) {
         if (lane == 0) {
@@ -642,30 +694,36 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
 #pragma unroll 1
             for (int it = 0; it < n_my; ++it) {
                 const int s = it & 1;
+                const bool tr = (it == kTraceItem) && p.trace != nullptr;
                 // ---- S(it) = Q K^T, as soon as the operands are in and O(it - 1) has left tensor memory
-                mbar_wait(&bars[kB2FullQK + s], (it >> 1) & 1);
-                if (it > 0) mbar_wait(&bars[kB2TmemFree], (it - 1) & 1);
+                mbar_wait_c(&bars[kB2FullQK + s], (it >> 1) & 1);
+                if (tr) p.trace[cta_id * 32 + 10] = clock64();
+                if (it > 0) mbar_wait_c(&bars[kB2TmemFree], (it - 1) & 1);
+                if (tr) p.trace[cta_id * 32 + 11] = clock64();
                 tc_fence_after();
                 mma_tile_x_rows(tmem, sm_q0 + s * kBlkBytes, sm_k, nk);
                 umma_commit(&bars[kB2SReady]);
                 // ---- Q, K of item it + 1: the other Q slot is free once the epilogue of item it - 1 has drained it,
                 // K once S(it) has retired and the edge warp has taken its dot products
                 if (it + 1 < n_my) {
-                    if (it >= 1) mbar_wait(&bars[kB2Done + (s ^ 1)], ((it - 1) >> 1) & 1);
-                    mbar_wait(&bars[kB2SReady], it & 1);
-                    mbar_wait(&bars[kB2EdgeK], it & 1);
+                    if (it >= 1) mbar_wait_c(&bars[kB2Done + (s ^ 1)], ((it - 1) >> 1) & 1);
+                    mbar_wait_c(&bars[kB2SReady], it & 1);
+                    mbar_wait_c(&bars[kB2EdgeK], it & 1);
                     load_qk(it + 1);
                 }
+                if (tr) p.trace[cta_id * 32 + 12] = clock64();
                 // ---- O(it) = P V with A = P from tensor memory, keys >= 128 first
-                mbar_wait(&bars[kB2FullV], it & 1);
+                mbar_wait_c(&bars[kB2FullV], it & 1);
                 if (ksteps > 8) {
-                    mbar_wait(&bars[kB2PHi], it & 1);
+                    mbar_wait_c(&bars[kB2PHi], it & 1);
                     tc_fence_after();
                     for (int ks = 8; ks < ksteps; ++ks)
                         umma_f16_ts(tmem + kFwdColO, tmem + kFwdColPHi + (ks - 8) * 8,
                                     umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)), idesc_pv, ks != 8);
                 }
-                mbar_wait(&bars[kB2PLo], it & 1);
+                if (tr) p.trace[cta_id * 32 + 13] = clock64();
+                mbar_wait_c(&bars[kB2PLo], it & 1);
+                if (tr) p.trace[cta_id * 32 + 14] = clock64();
                 tc_fence_after();
                 for (int ks = 0; ks < min(ksteps, 8); ++ks)
                     umma_f16_ts(tmem + kFwdColO, tmem + ks * 8, umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)),
@@ -673,16 +731,21 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
                 umma_commit(&bars[kB2OReady]);
                 // ---- V of item it + 1 once P V has retired and the edge warp has finished its row
                 if (it + 1 < n_my) {
-                    mbar_wait(&bars[kB2OReady], it & 1);
-                    mbar_wait(&bars[kB2EdgeV], it & 1);
+                    mbar_wait_c(&bars[kB2OReady], it & 1);
+                    if (tr) p.trace[cta_id * 32 + 15] = clock64();
+                    mbar_wait_c(&bars[kB2EdgeV], it & 1);
                     load_v(it + 1);
+                    if (tr) p.trace[cta_id * 32 + 16] = clock64();
                 }
             }
         }
     } else if (warp < 4) {
         const int r = warp * 32 + lane;  // query row in the tile == TMEM lane
         const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-        const int nk32 = (nk + 31) & ~31;
+        const int nch = (nk + 31) >> 5;       // 32-column chunks of S
+        const int n_hi = max(nch - 4, 0);      // chunks of keys >= 128
+        float sx_next = 0.f;
+        bool have_sx = false;
 #pragma unroll 1
         for (int it = 0; it < n_my; ++it) {
             const int s = it & 1;
@@ -691,24 +754,72 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
             uint8_t* sm_q = sm_q0 + s * kBlkBytes;
             const float* kx = xvec + 192 * s;
             const float* vx = kx + 64;
-            const bool tr = (it == 1) && warp == 0 && p.trace != nullptr && lane == 0;
+            const bool tr = (it == kTraceItem) && warp == 0 && p.trace != nullptr && lane == 0;
+            if (it == kTraceItem + 1 && warp == 0 && p.trace != nullptr && lane == 0) p.trace[cta_id * 32 + 9] = clock64();
             if (tr) p.trace[cta_id * 32 + 0] = clock64();
-            mbar_wait(&bars[kB2XReady + s], (it >> 1) & 1);
-            mbar_wait(&bars[kB2FullQK + s], (it >> 1) & 1);
-            const float sx = row_dot(sm_q, r, kx);  // score against the edge key, while the MMA runs
-            mbar_wait(&bars[kB2SReady], it & 1);
+            // score against the edge key: normally taken one item ahead (below, while O = P V runs)
+            float sx = sx_next;
+            if (!have_sx) {
+                mbar_wait_c(&bars[kB2XReady + s], (it >> 1) & 1);
+                mbar_wait_c(&bars[kB2FullQK + s], (it >> 1) & 1);
+                sx = row_dot(sm_q, r, kx);
+            }
+            have_sx = false;
+            mbar_wait_c(&bars[kB2SReady], it & 1);
             tc_fence_after();
             if (tr) p.trace[cta_id * 32 + 4] = clock64();
-            const float mx = fwd_row_max(trow, nk32, nv, sx);
+            // row max over all S columns (32 at a time, the next load in flight behind the reduction)
+            uint32_t va[32], vb[32];
+            float mx = sx;
+            tmem_ld<32>(trow, va);
+#pragma unroll 1
+            for (int i = 0; i < nch; i += 2) {
+                tmem_wait_ld();
+                if (i + 1 < nch) tmem_ld<32>(trow + 32 * (i + 1), vb);
+                mask_cols32(va, 32 * i, nv);
+                mx = max32(va, mx);
+                if (i + 1 < nch) {
+                    tmem_wait_ld();
+                    if (i + 2 < nch) tmem_ld<32>(trow + 32 * (i + 2), va);
+                    mask_cols32(vb, 32 * (i + 1), nv);
+                    mx = max32(vb, mx);
+                }
+            }
             const float mb = mx * kLog2e;
             if (tr) p.trace[cta_id * 32 + 5] = clock64();
+            // P = exp2(S log2e - mb) as packed bf16 over consumed S columns: the chunks of keys >= 128 first (into
+            // columns [128, 192)), then keys < 128 (into [0, 64)); a store never reaches a column not yet loaded
             float sum = 0.f;
-            if (nk32 > 128) sum = fwd_row_exp(trow, 128, nk32, kFwdColPHi, nv, mb, sum);
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[kB2PHi]);
-            sum = fwd_row_exp(trow, 0, min(nk32, 128), 0, nv, mb, sum);
+            auto col_of = [&](int i) { return i < n_hi ? 128 + 32 * i : 32 * (i - n_hi); };
+            auto pcol_of = [&](int i) { return i < n_hi ? kFwdColPHi + 16 * i : 16 * (i - n_hi); };
+            auto chunk_done = [&](int i) {
+                if (i == n_hi - 1) {  // every key >= 128 is stored: the issuing thread may start O += P_hi V_hi
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[kB2PHi]);
+                }
+            };
+            if (n_hi == 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kB2PHi]);
+            }
+            tmem_ld<32>(trow + col_of(0), va);
+#pragma unroll 1
+            for (int i = 0; i < nch; i += 2) {
+                tmem_wait_ld();
+                if (i + 1 < nch) tmem_ld<32>(trow + col_of(i + 1), vb);
+                mask_cols32(va, col_of(i), nv);
+                sum = exp32(va, mb, trow + pcol_of(i), sum);
+                chunk_done(i);
+                if (i + 1 < nch) {
+                    tmem_wait_ld();
+                    if (i + 2 < nch) tmem_ld<32>(trow + col_of(i + 2), va);
+                    mask_cols32(vb, col_of(i + 1), nv);
+                    sum = exp32(vb, mb, trow + pcol_of(i + 1), sum);
+                    chunk_done(i + 1);
+                }
+            }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -718,7 +829,14 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
             sum += px;
             if (q0 + r < nv) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + q0 + r] = mx + logf(sum);
             const float inv = 1.0f / sum;
-            mbar_wait(&bars[kB2OReady], it & 1);
+            // the tensor pipe needs ~1000 clk for O: take the next item's edge score now if its Q tile and edge vectors
+            // have already landed (they usually have; both barriers stay complete until this warp's item it + 1)
+            if (it + 1 < n_my && mbar_try_wait(&bars[kB2XReady + (s ^ 1)], ((it + 1) >> 1) & 1) &&
+                mbar_try_wait(&bars[kB2FullQK + (s ^ 1)], ((it + 1) >> 1) & 1)) {
+                sx_next = row_dot(sm_q0 + (s ^ 1) * kBlkBytes, r, xvec + 192 * (s ^ 1));
+                have_sx = true;
+            }
+            mbar_wait_c(&bars[kB2OReady], it & 1);
             tc_fence_after();
             if (tr) p.trace[cta_id * 32 + 7] = clock64();
             uint32_t v[64];
@@ -745,17 +863,20 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
             }
             __syncwarp();
             bf16* gout = p.out + static_cast<size_t>(n) * p.T * D + h * kHd;
+            // Pull the staged rows back into registers, hand the Q slot back to the TMA unit, then store.  (The reads
+            // have returned this warp's own staging writes, so those are performed; a fence.proxy.async here would
+            // compile to MEMBAR.ALL.CTA and sit behind the global stores for ~1500 clk.)
+            uint4 st[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                st[i] = *reinterpret_cast<const uint4*>(sm_q + row_chunk(warp * 32 + i * 4 + (lane >> 3), lane & 7));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2Done + s]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = warp * 32 + i * 4 + (lane >> 3), ch = lane & 7;
-                if (q0 + row < nv)
-                    *reinterpret_cast<uint4*>(gout + static_cast<size_t>(q0 + row) * D + ch * 8) =
-                        *reinterpret_cast<const uint4*>(sm_q + row_chunk(row, ch));
+                if (q0 + row < nv) *reinterpret_cast<uint4*>(gout + static_cast<size_t>(q0 + row) * D + ch * 8) = st[i];
             }
-            // this warp's rows of the Q slot (written above with ordinary stores) go back to the TMA unit
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[kB2Done + s]);
             if (tr) p.trace[cta_id * 32 + 8] = clock64();
         }
     } else {
@@ -771,27 +892,29 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
             float* vx = kx + 64;
             float* qx = kx + 128;
             // slot s was last read by the softmax warps of item it - 2
-            if (it >= 2) mbar_wait(&bars[kB2Done + s], ((it - 2) >> 1) & 1);
+            if (it >= 2) mbar_wait_c(&bars[kB2Done + s], ((it - 2) >> 1) & 1);
             qx[2 * lane] = bf_lo(xq), qx[2 * lane + 1] = bf_hi(xq);
             kx[2 * lane] = bf_lo(xk), kx[2 * lane + 1] = bf_hi(xk);
             vx[2 * lane] = bf_lo(xv), vx[2 * lane + 1] = bf_hi(xv);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kB2XReady + s]);
+            const float sxx = warp_sum(fmaf(bf_lo(xq), bf_lo(xk), bf_hi(xq) * bf_hi(xk)));  // q_x . k_x
             if (it + 1 < n_my) load_x(it + 1, xq, xk, xv);
-            mbar_wait(&bars[kB2FullQK + s], (it >> 1) & 1);
+            const bool tr = (it == kTraceItem) && p.trace != nullptr && lane == 0;
+            if (tr) p.trace[cta_id * 32 + 20] = clock64();
+            mbar_wait_c(&bars[kB2FullQK + s], (it >> 1) & 1);
+            if (tr) p.trace[cta_id * 32 + 21] = clock64();
             float sc[8];
-            float sxx = 0.f;
             if (has_edge_row) {
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
                     const int j = lane + 32 * jj;
                     sc[jj] = (j < nv) ? row_dot(sm_k, j, qx) : -INFINITY;
                 }
-#pragma unroll
-                for (int d = 0; d < 64; ++d) sxx = fmaf(qx[d], kx[d], sxx);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kB2EdgeK]);
+            if (tr) p.trace[cta_id * 32 + 22] = clock64();
             if (has_edge_row) {
                 float mx = sxx;
 #pragma unroll
@@ -808,21 +931,23 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
                 const float exx = exp2f(fmaf(sxx, kLog2e, -mb));
                 const float sum = warp_sum(part) + exx;
                 __syncwarp();
-                mbar_wait(&bars[kB2FullV], it & 1);
+                mbar_wait_c(&bars[kB2FullV], it & 1);
                 edge_gemv(pbuf, sm_v, nv, exx, vx, p.out + (static_cast<size_t>(n) * p.T + nv) * D + h * kHd, 1.0f / sum,
                           lane);
                 if (lane == 0) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + nv] = mx + logf(sum);
             } else {
                 // no row to compute, but still keep step with the V loads: the arrival below must not run a phase
                 // ahead of the issuing thread's wait for it (V of item it + 1 is only requested after that wait)
-                mbar_wait(&bars[kB2FullV], it & 1);
+                mbar_wait_c(&bars[kB2FullV], it & 1);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kB2EdgeV]);
+            if (tr) p.trace[cta_id * 32 + 23] = clock64();
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[cta_id * 32 + 31] = clock64();
     if (warp == 4) tmem_dealloc(tmem, 256);
 }
 

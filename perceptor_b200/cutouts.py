@@ -49,6 +49,28 @@ def whole_image_cutouts(batch: int, height: int, width: int) -> np.ndarray:
     return rows
 
 
+def validate_rows(rows: np.ndarray, batch: int, height: int, width: int) -> np.ndarray:
+    """Check caller-supplied cutout rows against the image batch they index; returns them as contiguous int32.
+
+    The sampler kernels address `images + ((b*3 + c)*H + y0 + dy)*W + x0 + dx` straight from the device table and the
+    backward scatter-adds into the same addresses, so a row outside the batch would read and WRITE out of bounds.
+    Rows are [n,4] (b, y0, x0, size) or [n,5] (b, y0, x0, h, w)."""
+    rows = np.asarray(rows)
+    if rows.ndim != 2 or rows.shape[1] not in (4, 5) or not np.issubdtype(rows.dtype, np.integer):
+        raise ValueError(f"cutout rows must be an integer array of shape [n,4] or [n,5], got {rows.dtype} {rows.shape}")
+    r = rows.astype(np.int64, copy=False)
+    if r.shape[0]:
+        b, y0, x0 = r[:, 0], r[:, 1], r[:, 2]
+        h = r[:, 3]
+        w = r[:, 3] if r.shape[1] == 4 else r[:, 4]
+        bad = (b < 0) | (b >= batch) | (y0 < 0) | (x0 < 0) | (h < 1) | (w < 1) | (y0 + h > height) | (x0 + w > width)
+        if bad.any():
+            i = int(np.flatnonzero(bad)[0])
+            raise ValueError(f"cutout row {i} = {rows[i].tolist()} does not fit a batch of {batch} images of "
+                             f"{height}x{width} (need 0 <= b < B, y0, x0 >= 0, sizes >= 1, y0 + h <= H, x0 + w <= W)")
+    return np.ascontiguousarray(rows, dtype=np.int32)
+
+
 def shard_rows(n_rows: int, rank: int, world: int) -> slice:
     """Contiguous block of cutout rows owned by `rank` (§8e: every rank builds the same table, then slices it)."""
     if not (0 <= rank < world):
@@ -56,3 +78,13 @@ def shard_rows(n_rows: int, rank: int, world: int) -> slice:
     base, rem = divmod(n_rows, world)
     start = rank * base + min(rank, rem)
     return slice(start, start + base + (1 if rank < rem else 0))
+
+
+def local_rows(rows: np.ndarray, rank: int, world: int, b_offset: int = 0) -> np.ndarray:
+    """The shard of `rank` with the image index re-based by `b_offset` (image-sharded mode: the rank holds only the
+    images [b_offset, b_offset + B_local) of the global batch the table was drawn for)."""
+    local = rows[shard_rows(rows.shape[0], rank, world)]
+    if b_offset:
+        local = local.copy()
+        local[:, 0] -= b_offset
+    return local

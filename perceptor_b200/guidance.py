@@ -51,6 +51,9 @@ class _GraphSlot:
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         self.d_images = torch.zeros_like(images)
         self.stash = torch.empty(engine.stash_bytes(plan.n_local), dtype=torch.uint8, device=dev)
+        # the captured graphs bake this pointer in, so the slot owns its scratch memory: the engine-wide workspace of
+        # the eager path may be reallocated by a later, larger call
+        self.ws = torch.empty(engine.workspace_bytes(plan.n_local), dtype=torch.uint8, device=dev)
         self.fwd_graph: torch.cuda.CUDAGraph | None = None
         self.bwd_graph: torch.cuda.CUDAGraph | None = None
         self.calls_fwd = 0
@@ -94,12 +97,13 @@ class GuidanceEngine:
     def _method_for_size(self, s: int) -> int:
         return LANCZOS3 if s >= self.shape.image_size else CUBIC
 
-    def plan_cutouts(self, rows: np.ndarray, rank: int = 0, world: int = 1) -> CutPlan:
-        """rows: [N,4] square cutouts (b,y0,x0,size) or [N,5] boxes (b,y0,x0,h,w)."""
+    def plan_cutouts(self, rows: np.ndarray, rank: int = 0, world: int = 1, b_offset: int = 0) -> CutPlan:
+        """rows: [N,4] square cutouts (b,y0,x0,size) or [N,5] boxes (b,y0,x0,h,w) of ALL ranks; this rank takes the
+        contiguous shard `cutouts.shard_rows(N, rank, world)`.  `b_offset` re-bases the image index of the shard when
+        the rank holds only its own images (image-sharded mode: global image b is local image b - b_offset)."""
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         n_total = rows.shape[0]
-        sl = cutouts.shard_rows(n_total, rank, world)
-        local = rows[sl]
+        local = cutouts.local_rows(rows, rank, world, b_offset)
         r = self.shape.image_size
         dev = np.zeros((local.shape[0], native.CUT_STRIDE), dtype=np.int32)
         if local.shape[0]:
@@ -123,14 +127,17 @@ class GuidanceEngine:
         table = torch.from_numpy(dev).pin_memory().to(self.device, non_blocking=True) if local.shape[0] else \
             torch.zeros((0, native.CUT_STRIDE), dtype=torch.int32, device=self.device)
         max_in_w = int(dev[:, 4].max()) if local.shape[0] else 1
-        return CutPlan(rows, table, n_total, local.shape[0], max_in_w, tabs_c, tab_tensors)
+        return CutPlan(rows if not b_offset else local, table, n_total, local.shape[0], max_in_w, tabs_c, tab_tensors)
 
     def prebuild_tables(self, min_size: int, max_size: int) -> None:
         self.tables.ensure_sizes(range(min_size, max_size + 1), self._method_for_size)
 
     # ------------------------------------------------------------------ buffers
+    def workspace_bytes(self, n: int) -> int:
+        return native.lib().pcg_workspace_bytes(C.byref(self.weights.cfg), n)
+
     def _get_workspace(self, n: int) -> torch.Tensor:
-        need = native.lib().pcg_workspace_bytes(C.byref(self.weights.cfg), n)
+        need = self.workspace_bytes(n)
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = None
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -158,7 +165,7 @@ class GuidanceEngine:
     def forward(self, images: torch.Tensor, plan: CutPlan, targets, tweights, loss_scale: float, want_grad: bool,
                 want_enc: bool, normalize: bool = True):
         """Returns (loss_sum [1] f32 or None, enc [n,E] f32 or None, stash or None)."""
-        self._check_images(images)
+        self._check_images(images, plan)
         lib = native.lib()
         n = plan.n_local
         loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device) if targets is not None else None
@@ -194,7 +201,6 @@ class GuidanceEngine:
         """The graph slot matching this call, (re)built when the configuration changes; None when graphs do not apply."""
         if not self.use_graphs or plan.n_local == 0 or torch.cuda.is_current_stream_capturing():
             return None
-        ws = self._get_workspace(plan.n_local)
         # graphs bake the resize-table pointers in: build every table a crop of this image can need up front, so that
         # the device copy is uploaded once and never moves (table ids are append-only, older plans stay valid)
         side = int(max(images.shape[2], images.shape[3]))
@@ -203,16 +209,17 @@ class GuidanceEngine:
             self._prebuilt_side = side
         tabs = self.tables.device_tensors(self.device)
         key = (tuple(images.shape), plan.n_local, plan.n_total, tuple(targets.shape), float(loss_scale),
-               tuple(t.data_ptr() for t in tabs), ws.data_ptr())
+               tuple(t.data_ptr() for t in tabs))
+        if self._slot is not None and self._slot.busy():
+            # a forward is still waiting for its backward: its activations (and, if the configuration differs, its
+            # whole slot: the pending backward replays graphs that point into it) must stay; this call runs eagerly
+            return None
         if key != self._slot_key:
             self._slot = None  # frees the previous slot's stash before the new one is allocated
             self._slot_key = None
             self._slot = _GraphSlot(self, images, plan, targets, tweights)
             self._slot_key = key
-        slot = self._slot
-        if slot.busy():  # a forward is still waiting for its backward: do not clobber its activations
-            return None
-        return slot
+        return self._slot
 
     def _slot_plan(self, slot: _GraphSlot, plan: CutPlan, width: int) -> CutPlan:
         # the sampler's launch geometry depends on the widest crop: fix it at the image width so one graph fits all;
@@ -225,14 +232,14 @@ class GuidanceEngine:
     def forward_graphed(self, slot: _GraphSlot, images, plan: CutPlan, targets, tweights, loss_scale: float, token):
         """Loss forward (activations kept) through the slot.  The first call runs eagerly on the static buffers, the
         second captures, later ones replay."""
-        self._check_images(images)
+        self._check_images(images, plan)
         lib = native.lib()
         slot.images.copy_(images)
         slot.table.copy_(plan.table)
         slot.targets.copy_(targets)
         slot.tweights.copy_(tweights)
         splan = self._slot_plan(slot, plan, images.shape[3])
-        ws = self._get_workspace(plan.n_local)
+        ws = slot.ws
 
         def launch():
             slot.loss_sum.zero_()
@@ -260,7 +267,7 @@ class GuidanceEngine:
     def backward_graphed(self, slot: _GraphSlot, plan: CutPlan, loss_scale: float) -> torch.Tensor:
         lib = native.lib()
         splan = self._slot_plan(slot, plan, slot.images.shape[3])
-        ws = self._get_workspace(plan.n_local)
+        ws = slot.ws
 
         def launch():
             slot.d_images.zero_()
@@ -286,11 +293,14 @@ class GuidanceEngine:
         self.launches_bwd = slot.launches_bwd
         return slot.d_images.clone()
 
-    def _check_images(self, images: torch.Tensor) -> None:
+    def _check_images(self, images: torch.Tensor, plan: CutPlan | None = None) -> None:
         if images.dim() != 4 or images.shape[1] != 3:
             raise ValueError(f"images must be [N,3,H,W], got {tuple(images.shape)}")
         if images.device != self.device or images.dtype != torch.float32 or not images.is_contiguous():
             raise ValueError("images must be contiguous float32 on the engine's CUDA device")
+        if plan is not None:
+            # the kernels index the images (and scatter-add into their gradient) straight from the cutout table
+            cutouts.validate_rows(plan.rows, images.shape[0], images.shape[2], images.shape[3])
 
 
 def _all_reduce_sum(t: torch.Tensor, group) -> None:
@@ -302,8 +312,13 @@ class GuidanceLossFn(torch.autograd.Function):
     """loss = multiplier * mean_{n,m}(w_m * d(e_n, t_m)) over ALL ranks' cutouts; gradient into `images`."""
 
     @staticmethod
-    def forward(ctx, images, engine: GuidanceEngine, plan: CutPlan, targets, tweights, multiplier, group):
+    def forward(ctx, images, engine: GuidanceEngine, plan: CutPlan, targets, tweights, multiplier, group,
+                reduce_grad=True):
+        """`reduce_grad`: the image gradient is summed over the group (cutout-sharded mode: every rank holds every
+        image).  False in image-sharded mode, where a rank's cutouts only touch its own images: the step then has no
+        data-path collective except the scalar loss."""
         want_grad = ctx.needs_input_grad[0]
+        ctx.reduce_grad = bool(reduce_grad)
         scale = float(multiplier) / float(plan.n_total * targets.shape[0])
         slot = engine._slot_for(images, plan, targets, tweights, scale) if want_grad else None
         ctx.slot, ctx.token = slot, None
@@ -326,8 +341,9 @@ class GuidanceLossFn(torch.autograd.Function):
         else:
             d_images = ctx.engine.backward(ctx.images_shape, ctx.plan, ctx.stash, ctx.targets, ctx.tweights, ctx.scale)
         ctx.stash = None
-        _all_reduce_sum(d_images, ctx.group)
-        return d_images * grad_out, None, None, None, None, None, None
+        if ctx.reduce_grad:
+            _all_reduce_sum(d_images, ctx.group)
+        return d_images * grad_out, None, None, None, None, None, None, None
 
 
 class EncodeImagesFn(torch.autograd.Function):

@@ -3,8 +3,12 @@
 API parity (perceptor/losses/clip/clip.py:10-99, perceptor/losses/open_clip.py:7-97): construct with a model name,
 `add_texts_` / `add_images_` / `add_encodings_` / `add_text_off_` / `mul_` return self, `encodings` / `weights` are
 frozen nn.Parameters rebuilt by torch.cat, `forward(images[N,3,H,W])` returns a 0-d loss whose autograd gradient
-flows into `images`.  Keyword-only extras (n_cutouts, cut_pow, min_size, max_size, seed/generator, process_group)
-default to the reference behaviour: every whole image is resized and encoded.
+flows into `images`.  Keyword-only extras (n_cutouts, cut_pow, min_size, max_size, seed/generator, process_group,
+shard) default to the reference behaviour: every whole image is resized and encoded.
+
+Multi-GPU (`process_group=`): `shard="cutouts"` (default) -- every rank passes the SAME images, the cutout table is
+split over the ranks and the image gradient is summed with one all-reduce; `shard="images"` -- every rank passes its
+OWN images (same count and size), the loss is the mean over all ranks' cutouts and the gradient needs no collective.
 """
 from __future__ import annotations
 
@@ -24,7 +28,10 @@ class _TextImageLoss(torch.nn.Module):
 
     _renormalize_targets = True
 
-    def _init_guidance(self, n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group):
+    def _init_guidance(self, n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group, shard="cutouts"):
+        if shard not in ("cutouts", "images"):
+            raise ValueError(f"shard must be 'cutouts' or 'images', got {shard!r}")
+        self.shard = shard
         self.n_cutouts = n_cutouts
         self.cut_pow = float(cut_pow)
         self.min_size = min_size
@@ -67,6 +74,9 @@ class _TextImageLoss(torch.nn.Module):
     # ------------------------------------------------------------------------------------------------
     def _cutout_rows(self, images) -> np.ndarray:
         b, _, h, w = images.shape
+        return self._cutout_rows_for(b, h, w)
+
+    def _cutout_rows_for(self, b: int, h: int, w: int) -> np.ndarray:
         if self.n_cutouts is None:
             return cutouts.whole_image_cutouts(b, h, w)
         return cutouts.sample_cutouts(self.generator, b, h, w, int(self.n_cutouts), self.cut_pow, self.min_size,
@@ -84,18 +94,29 @@ class _TextImageLoss(torch.nn.Module):
         rank = world = None
         if group is not None:
             rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+        targets = self.encodings.detach().to(eng.device, torch.float32).contiguous()
+        tweights = self.weights.detach().to(eng.device, torch.float32).contiguous()
+        if group is not None and world > 1 and self.shard == "images":
+            # image-sharded: every rank passes ITS images (the same count and size on every rank).  The table is drawn
+            # for the concatenated batch from the common seed, so the result equals the single-process loss over all
+            # ranks' images; a rank's cutouts touch only its own images, so the gradient needs no collective.
+            b_local = images.shape[0]
+            rows = self._cutout_rows_for(b_local * world, images.shape[2], images.shape[3])
+            if rows.shape[0] % world != 0:
+                raise ValueError("image-sharded mode needs the same number of cutouts on every rank")
+            self.last_cutouts = rows
+            plan = eng.plan_cutouts(rows, rank, world, b_offset=rank * b_local)
+            return GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, False)
         rows = self._cutout_rows(images)
         self.last_cutouts = rows
         plan = eng.plan_cutouts(rows, rank or 0, world or 1)
-        targets = self.encodings.detach().to(eng.device, torch.float32).contiguous()
-        tweights = self.weights.detach().to(eng.device, torch.float32).contiguous()
-        return GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group)
+        return GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, True)
 
 
 class CLIP(_TextImageLoss):
     def __init__(self, name="ViT-B-32", precision="fp32", jit=False, *, n_cutouts=None, cut_pow=1.0, min_size=None,
-                 max_size=None, seed=0, generator=None, process_group=None, state_dict=None, weights_seed=0,
-                 bpe_path=None):
+                 max_size=None, seed=0, generator=None, process_group=None, shard="cutouts", state_dict=None,
+                 weights_seed=0, bpe_path=None):
         """
         Args:
             name: name of the clip model. Available models on the native path:
@@ -108,7 +129,7 @@ class CLIP(_TextImageLoss):
         self.name = name
         extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
         self.model = models.CLIP(name, precision, bpe_path=bpe_path, **extra)
-        self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group)
+        self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group, shard)
         self.multiplier = 0.01 if name in ("ViT-L-14", "ViT-L-14-336") else 1.0
 
     def mul_(self, multiplier):
@@ -129,8 +150,8 @@ class OpenCLIP(_TextImageLoss):
     _renormalize_targets = False  # perceptor/losses/open_clip.py:58-85 stores encodings as given
 
     def __init__(self, architecture="ViT-L-14", weights="laion2b_s32b_b82k", *, n_cutouts=None, cut_pow=1.0,
-                 min_size=None, max_size=None, seed=0, generator=None, process_group=None, state_dict=None,
-                 weights_seed=0, bpe_path=None):
+                 min_size=None, max_size=None, seed=0, generator=None, process_group=None, shard="cutouts",
+                 state_dict=None, weights_seed=0, bpe_path=None):
         """
         Args:
             architecture (str): name of the clip model
@@ -142,7 +163,7 @@ class OpenCLIP(_TextImageLoss):
         self.architecture = architecture
         extra = {"seed": weights_seed} if state_dict is None else {"state_dict": state_dict}
         self.model = models.OpenCLIP(architecture, weights, bpe_path=bpe_path, **extra)
-        self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group)
+        self._init_guidance(n_cutouts, cut_pow, min_size, max_size, seed, generator, process_group, shard)
 
     def forward(self, images):
         return self._loss(images, 1.0)

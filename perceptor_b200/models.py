@@ -112,6 +112,8 @@ class _OpenCLIP(torch.nn.Module):
         images = images.contiguous()
         if cutout_rows is None:
             cutout_rows = cutouts.whole_image_cutouts(images.shape[0], images.shape[2], images.shape[3])
+        else:
+            cutout_rows = cutouts.validate_rows(cutout_rows, images.shape[0], images.shape[2], images.shape[3])
         plan = eng.plan_cutouts(np.asarray(cutout_rows))
         return EncodeImagesFn.apply(images, eng, plan, bool(normalize))
 

@@ -70,3 +70,36 @@ def test_two_rank_sharding_reproduces_single_process(tmp_path):
     loss, grad = _shard_loss_and_grad(rows.tolist(), rows.shape[0], images, targets, weights, tiny_state_dict())
     assert abs(float(r0["loss"][0]) - float(loss)) <= 1e-6 * abs(float(loss))
     assert float(np.abs(r0["grad"] - grad.numpy()).max()) <= 1e-6 * float(grad.abs().max()) + 1e-9
+
+
+def _worker_images(rank, world, port, out_dir):
+    """shard="images": the rank holds ONLY its own image; the table is drawn for the concatenated batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    images, targets, weights = _inputs()
+    mine = images[rank:rank + 1]
+    sd = tiny_state_dict()
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(11), world, H, W, 6, 1.0, 16, 40)
+    local = cutouts.local_rows(rows, rank, world, b_offset=rank)
+    cutouts.validate_rows(local, 1, H, W)  # every local row addresses the one local image
+    loss, grad = _shard_loss_and_grad(local.tolist(), rows.shape[0], mine, targets, weights, sd)
+    loss = loss.reshape(1).clone()
+    _all_reduce_sum(loss, dist.group.WORLD)  # the only collective of the step
+    np.savez(os.path.join(out_dir, f"img_rank{rank}.npz"), loss=loss.numpy(), grad=grad.numpy(), rows=rows)
+    dist.destroy_process_group()
+
+
+def test_two_rank_image_sharding_needs_no_gradient_collective(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_images, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "img_rank0.npz"), np.load(tmp_path / "img_rank1.npz")
+    assert np.array_equal(r0["rows"], r1["rows"]) and np.array_equal(r0["loss"], r1["loss"])
+    images, targets, weights = _inputs()
+    rows = r0["rows"]
+    loss, grad = _shard_loss_and_grad(rows.tolist(), rows.shape[0], images, targets, weights, tiny_state_dict())
+    assert abs(float(r0["loss"][0]) - float(loss)) <= 1e-6 * abs(float(loss))
+    both = np.concatenate([r0["grad"], r1["grad"]])  # rank r's gradient IS the gradient of image r
+    assert float(np.abs(both - grad.numpy()).max()) <= 1e-6 * float(grad.abs().max()) + 1e-9

@@ -200,3 +200,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
     assert d["config"]["workload"] == "vit_b32_224_16cut_256px" and d["metric"].startswith("CLIP-guidance cutouts/sec")
+
+
+def test_validate_rows_rejects_out_of_bounds():
+    """Caller-supplied cutout rows index the image (and its gradient) on the device: anything outside must raise."""
+    from perceptor_b200 import cutouts
+    ok = np.array([[0, 0, 0, 32], [1, 8, 16, 24]], dtype=np.int32)
+    assert cutouts.validate_rows(ok, 2, 32, 40).dtype == np.int32
+    assert cutouts.validate_rows(np.array([[0, 0, 0, 32, 40]]), 1, 32, 40).shape == (1, 5)
+    assert cutouts.validate_rows(np.zeros((0, 4), dtype=np.int64), 1, 8, 8).shape == (0, 4)
+    for bad in ([[2, 0, 0, 8]], [[-1, 0, 0, 8]], [[0, -1, 0, 8]], [[0, 0, -3, 8]], [[0, 0, 0, 0]], [[0, 25, 0, 8]],
+                [[0, 0, 33, 8]], [[0, 0, 0, 33]], [[0, 0, 0, 8, 41]], [[0, 30, 0, 3, 8]]):
+        with pytest.raises(ValueError):
+            cutouts.validate_rows(np.array(bad), 2, 32, 40)
+    with pytest.raises(ValueError):
+        cutouts.validate_rows(np.zeros((2, 3), dtype=np.int32), 1, 8, 8)
+    with pytest.raises(ValueError):
+        cutouts.validate_rows(np.zeros((2, 4), dtype=np.float32), 1, 8, 8)
+
+
+def test_local_rows_rebases_image_index():
+    from perceptor_b200 import cutouts
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(3), 4, 64, 64, 5, 1.0, 16, 64)
+    for rank in range(4):
+        loc = cutouts.local_rows(rows, rank, 4, b_offset=rank)
+        assert loc.shape == (5, 4) and (loc[:, 0] == 0).all()
+        assert np.array_equal(loc[:, 1:], rows[rank * 5:(rank + 1) * 5, 1:])
+    assert np.array_equal(cutouts.local_rows(rows, 1, 2), rows[10:])

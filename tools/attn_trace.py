@@ -11,7 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perceptor_b200 import native, ops  # noqa: E402
 
 # persistent forward: stamps of each CTA's SECOND item (steady state), warp 0
-FWD2 = {0: "item start", 4: "S ready", 5: "max pass done", 6: "exp pass done", 7: "O ready", 8: "epilogue done"}
+FWD2 = {0: "item start", 9: "next item start", 4: "S ready", 5: "max pass done", 6: "exp pass done", 7: "O ready", 8: "epilogue done",
+        10: "ctl: Q+K landed", 11: "ctl: tmem free (S issue)", 12: "ctl: next Q+K requested", 13: "ctl: PV hi issued",
+        14: "ctl: P lo seen", 15: "ctl: O retired", 16: "ctl: next V requested", 20: "edge: vectors written",
+        21: "edge: K landed", 22: "edge: K dots done", 23: "edge: row done"}
 FWD = {0: "start", 1: "setup done", 2: "K+Q landed", 3: "V landed", 4: "S ready (w0)", 5: "max pass done", 6: "exp pass done",
        7: "O ready", 8: "epilogue done", 9: "edge row done", 10: "all warps done"}
 BWD = {0: "start", 1: "first loads landed", 2: "edge vectors ready", 3: "edge gemv done", 4: "b0 S/dP ready", 5: "b0 alu done",
@@ -74,7 +77,15 @@ def main():
     native.lib().pcg_attn_set_trace(trace.data_ptr())
     out, lse = ops.attn_fwd(qkv, n, t, h)
     torch.cuda.synchronize()
-    show(trace, FWD2 if args.persist else FWD, "forward (persistent, second item of each CTA)" if args.persist else "forward")
+    if args.persist:
+        tt = trace.cpu().double()
+        tt = tt[ttt[:, 30] > 0]
+        life = tt[:, 31] - tt[:, 30]
+        span = float(tt[:, 31].max() - tt[:, 30].min())
+        print(f"persistent forward: {tt.shape[0]} CTAs, items per CTA {tt[:, 29].min():.0f}-{tt[:, 29].max():.0f}, CTA lifetime "
+              f"median {life.median():.0f} max {life.max():.0f} clk, per item {float((life / tt[:, 29]).median()):.0f} clk, "
+              f"grid span {span:.0f} clk")
+    show(trace, FWD2 if args.persist else FWD, "forward (persistent, one steady-state item of each CTA)" if args.persist else "forward")
     trace.zero_()
     ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
     torch.cuda.synchronize()
