@@ -79,12 +79,10 @@ def main():
     torch.cuda.synchronize()
     if args.persist:
         tt = trace.cpu().double()
-        tt = tt[ttt[:, 30] > 0]
+        tt = tt[tt[:, 30] > 0]
         life = tt[:, 31] - tt[:, 30]
-        span = float(tt[:, 31].max() - tt[:, 30].min())
         print(f"persistent forward: {tt.shape[0]} CTAs, items per CTA {tt[:, 29].min():.0f}-{tt[:, 29].max():.0f}, CTA lifetime "
-              f"median {life.median():.0f} max {life.max():.0f} clk, per item {float((life / tt[:, 29]).median()):.0f} clk, "
-              f"grid span {span:.0f} clk")
+              f"median {life.median():.0f} max {life.max():.0f} clk, per item {float((life / tt[:, 29]).median()):.0f} clk")
     show(trace, FWD2 if args.persist else FWD, "forward (persistent, one steady-state item of each CTA)" if args.persist else "forward")
     trace.zero_()
     ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
