@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (architecture, image H=W, cutouts per image, min cutout size, images per GPU)
     "vit_l14_224_128cut_512px": ("ViT-L-14", 512, 128, 128, 1),
+    # BASELINE configs[2] as SURVEY 8(d) fixes it (B = 1): ONE 512x512 image, its 128 cutouts sharded over the ranks
+    "vit_l14_224_128cut_512px_1image": ("ViT-L-14", 512, 128, 128, 0),
     "vit_b32_224_64cut_4x512px": ("ViT-B-32", 512, 64, 64, 4),
     "vit_l14_336_256cut_768px": ("ViT-L-14-336", 768, 256, 192, 1),
     # BASELINE configs[3] as written: ONE 768x768 image, 256 cutouts in total, sharded over the ranks (strong scaling)
@@ -36,11 +38,37 @@ WORKLOADS = {
     "vit_b32_224_16cut_256px": ("ViT-B-32", 256, 16, 64, 1),
 }
 DEFAULT_WORKLOAD = "vit_l14_224_128cut_512px"
-# dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05_kernel launch, mean over the eight GEMM shapes of one
-# transformer layer (forward qkv / out / fc / proj, backward dproj / dfc / dout / dqkv) from the `ncu --set full`
-# captures summarised in profiles/r01d_gemm_{fwd,bwd}_ncu_full.csv.  It equals the operand + epilogue bytes of those
-# shapes (no re-reads): e.g. out-proj reads A 67 MB + residual 135 MB = 204 MB measured.
-NCU_GEMM_TRAFFIC_BYTES = {"vit_l14_224_128cut_512px": 363.7e6}
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05_kernel launch, mean over the eight GEMM
+# shapes of one transformer layer (forward qkv / out / fc / proj, backward dproj / dfc / dout / dqkv), READ from the
+# committed `ncu --set full` summaries (tools/ncu_summ.py output) rather than typed in.
+NCU_GEMM_TRAFFIC_FILES = {"vit_l14_224_128cut_512px": ("profiles/r01d_gemm_fwd_ncu_full.csv",
+                                                       "profiles/r01d_gemm_bwd_ncu_full.csv")}
+
+
+def ncu_gemm_traffic(workload: str):
+    """(bytes per launch, source) from the committed ncu summaries, or (None, reason)."""
+    import csv
+    files = NCU_GEMM_TRAFFIC_FILES.get(workload)
+    if not files:
+        return None, "no ncu capture committed for this workload"
+    vals = []
+    for rel in files:
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            return None, f"{rel} missing"
+        with open(path) as f:
+            rows = [r for r in csv.reader(line for line in f if not line.startswith("#"))]
+        hdr = rows[0]
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        units = rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if len(r) > max(ri, wi) and "gemm_tcgen05_kernel" in r[ki]:
+                vals.append(float(r[ri].replace(",", "")) * scale.get(units[ri], 1.0)
+                            + float(r[wi].replace(",", "")) * scale.get(units[wi], 1.0))
+    if not vals:
+        return None, "no gemm_tcgen05_kernel rows in the ncu summaries"
+    return sum(vals) / len(vals), f"mean of {len(vals)} captured launches in {', '.join(files)}"
 METRIC = "CLIP-guidance cutouts/sec (loss + image grad), ViT-L/14, at 1/2/4/8 B200"
 
 
@@ -198,6 +226,40 @@ def run_reference(args, rank: int):
     emit(line)
 
 
+def parity_check(loss_mod, arch, shape, hw, min_size, device, n_check=4):
+    """The timed configuration against the CPU oracle, outside the timed region: the SAME encoder (weights, targets,
+    graph path) on a 4-cutout shard of the workload's cutout distribution.  Returns the loss relative error and the
+    image-gradient cosine (north_star's bars: 1e-2 and 0.999)."""
+    import numpy as np
+
+    from oracle import guidance as guidance_oracle
+    from perceptor_b200 import cutouts
+    from perceptor_b200.guidance import GuidanceLossFn
+
+    eng = loss_mod.model.engine()
+    g = torch.Generator().manual_seed(1234)
+    image = torch.rand(1, 3, hw, hw, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(99), 1, hw, hw, n_check, 1.0, min_size, hw)
+    targets = loss_mod.encodings.detach().float().cpu()
+    weights = loss_mod.weights.detach().float().cpu()
+    img = image.to(device).requires_grad_()
+    loss = GuidanceLossFn.apply(img, eng, eng.plan_cutouts(rows), loss_mod.encodings.detach().float().contiguous(),
+                                loss_mod.weights.detach().float().contiguous(), float(loss_mod.multiplier), None)
+    loss.backward()
+    sd = {k: v.detach().float().cpu() for k, v in loss_mod.model.state_dict_openai().items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_img = image.clone().requires_grad_()
+    ref = guidance_oracle.guidance_loss(ref_img, rows.tolist(), sd, shape.image_size, shape.patch, shape.layers,
+                                        shape.heads, targets, weights, float(loss_mod.multiplier))
+    ref.backward()
+    ga, gb = img.grad.detach().float().cpu().flatten().double(), ref_img.grad.flatten().double()
+    cos = float((ga @ gb) / (ga.norm() * gb.norm() + 1e-300))
+    rel = abs(float(loss.detach()) - float(ref.detach())) / max(abs(float(ref.detach())), 1e-30)
+    return {"loss_rel_err": rel, "grad_cosine": cos, "cutouts": int(n_check), "tolerance": {"loss_rel_err": 1e-2,
+            "grad_cosine": 0.999}, "ok": bool(rel <= 1e-2 and cos >= 0.999),
+            "what": f"{arch}, {n_check} cutouts of one {hw}x{hw} image through the timed encoder vs the fp32 CPU oracle"}
+
+
 # ------------------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------------------
@@ -220,13 +282,20 @@ def run_native(args, rank: int, world: int, local_rank: int):
     shape = SHAPES[arch]
     n_images = imgs_per_gpu * world if imgs_per_gpu > 0 else 1  # 0: one image in total, its cutouts sharded
     cutouts_per_step = n_images * n_cut
+    # weak scaling: every rank owns its images (shard="images": no gradient collective, only the scalar loss);
+    # strong scaling: one image, its cutouts split over the ranks, image gradient summed with one all-reduce
+    shard = "images" if imgs_per_gpu > 0 else "cutouts"
 
-    loss_mod = losses.CLIP(arch, n_cutouts=n_cut, min_size=min_size, max_size=hw, seed=0, process_group=group)
+    loss_mod = losses.CLIP(arch, n_cutouts=n_cut, min_size=min_size, max_size=hw, seed=0, process_group=group, shard=shard)
     g = torch.Generator().manual_seed(0)
-    loss_mod.add_encodings_(torch.randn(2, shape.embed, generator=g))
+    target_enc = torch.randn(2, shape.embed, generator=g)
+    loss_mod.add_encodings_(target_enc)
     eng = loss_mod.model.engine()
     eng.prebuild_tables(min_size, hw)
-    host_images = torch.rand(n_images, 3, hw, hw, generator=g).pin_memory()
+    all_images = torch.rand(n_images, 3, hw, hw, generator=g)
+    if shard == "images":  # this rank's images only: what it uploads and what it gets a gradient for
+        all_images = all_images[rank * imgs_per_gpu:(rank + 1) * imgs_per_gpu]
+    host_images = all_images.contiguous().pin_memory()
     dev_images = host_images.to(device)
     host_grad = torch.empty_like(host_images).pin_memory()
 
@@ -297,8 +366,34 @@ def run_native(args, rank: int, world: int, local_rank: int):
     e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
     e2e_value = cutouts_per_step / (e2e_ms * 1e-3)
 
+    # strong-scaling sub-record of the headline workload (C3 at B = 1): ONE image, the same 128 cutouts
+    # split over the ranks, gradient all-reduced.  Every rank runs it; at N = 1 it is the main measurement itself.
+    strong = None
+    if world > 1 and args.workload == DEFAULT_WORKLOAD and not args.no_strong:
+        s_arch, s_hw, s_cut, s_min, _ = WORKLOADS["vit_l14_224_128cut_512px_1image"]
+        strong_mod = losses.CLIP(s_arch, n_cutouts=s_cut, min_size=s_min, max_size=s_hw, seed=0, process_group=group,
+                                 shard="cutouts")
+        strong_mod.add_encodings_(target_enc)
+        one_image = torch.rand(1, 3, s_hw, s_hw, generator=torch.Generator().manual_seed(1)).to(device)
+
+        def step_strong():
+            img = one_image.detach().requires_grad_()
+            loss = strong_mod(img)
+            loss.backward()
+            return loss
+
+        for _ in range(max(args.warmup, 3)):
+            step_strong()
+        s_ms = timed(step_strong, args.steps) / args.steps
+        strong = {"workload": "vit_l14_224_128cut_512px_1image", "scaling": "strong", "n_gpus": world,
+                  "cutouts_per_step": s_cut, "cutouts_per_gpu": s_cut // world, "ms_per_step": s_ms,
+                  "value": s_cut / (s_ms * 1e-3), "unit": "cutouts/s",
+                  "note": "one 512x512 image, 128 cutouts sharded over the ranks, image gradient + loss all-reduced; "
+                          "device-timed, max over ranks, CUDA-graph replay"}
+
     if rank != 0:
         return
+    parity = parity_check(loss_mod, arch, shape, hw, min_size, device) if not args.no_parity else None
     peaks = measured_peaks()
     flops_per_cutout = shape.flops_per_cutout()
     step_tflops = value / world * flops_per_cutout / 1e12
@@ -309,6 +404,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
                     "rate": (v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("gemm", "attn_fwd", "attn_bwd") else 1e9))
                     if v["ms"] > 0 else 0.0} for k, v in prof.items()}
 
+    traffic, traffic_src = ncu_gemm_traffic(args.workload)
     cpu_value, cpu_med, cpu_done = time_cpu(arch, hw, min_size, args.cpu_sample, 2, 1) if not args.no_cpu else (None, None, 0)
     line = {
         "metric": METRIC, "value": value, "unit": "cutouts/s", "n_gpus": world, "steps": args.steps,
@@ -317,7 +413,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "model": arch, "images": n_images, "image": f"{hw}x{hw}",
                    "cutouts_per_image": n_cut, "cutouts_per_step": cutouts_per_step, "targets": 2,
-                   "parallelism": f"cutout-sharded dp{world}" if world > 1 else "single GPU",
+                   "parallelism": (f"image-sharded dp{world} (each rank its own image, no gradient collective)"
+                                   if shard == "images" else f"cutout-sharded dp{world} (gradient all-reduce)")
+                   if world > 1 else "single GPU",
                    "weights": "random-init (no network for checkpoints)",
                    "l2": "per-step working set (activation stash >= 19 GB for ViT-L/14 x128) >> 126 MB L2; no flush needed",
                    "launch": "CUDA-graph replay (forward graph + backward graph)" if graphs_on else "eager launches",
@@ -325,19 +423,22 @@ def run_native(args, rank: int, world: int, local_rank: int):
                    "kernel_families": families},
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "cutouts/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": host_images.numel() * 4 + cutouts_per_step // world * 32,
+                "h2d_bytes_per_step": host_images.numel() * 4 + cutouts_per_step // world * 32,  # per rank
                 "d2h_bytes_per_step": host_grad.numel() * 4 + 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": gemm_tflops, "peak": peak,
                      "unit": "TFLOP/s", "frac": gemm_tflops / peak,
-                     "traffic": NCU_GEMM_TRAFFIC_BYTES.get(args.workload),
-                     "traffic_unit": "bytes per launch (ncu dram read + write, mean over the layer's 8 GEMM shapes; "
-                                     "profiles/r01d_gemm_*_ncu_full.csv)",
+                     "traffic": traffic,
+                     "traffic_unit": f"bytes per launch (ncu dram read + write; {traffic_src})",
                      "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches_timed": gemm["count"], "share_of_step": gemm["ms"] / prof_ms,
                      "timing": "CUDA event pair around every launch, second pass over the same K steps "
                                f"({prof_ms / args.steps:.2f} ms/step with the events, eager launches)"},
     }
+    if strong is not None:
+        line["strong"] = strong
+    if parity is not None:
+        line["parity"] = parity
     if cpu_value is not None:
         line["cpu_baseline"] = {"value": cpu_value, "unit": "cutouts/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{args.cpu_sample} cutouts/step of the same workload, {cpu_done} timed steps "
@@ -356,6 +457,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument("--cpu-sample", type=int, default=8, help="cutouts per CPU-baseline step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check against the CPU oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -363,3 +363,173 @@ def test_cuda_graph_replay_matches_eager_launches(cuda_device):
     lg, gg = run(eng_g, rows)
     le, ge = run(eng_e, rows)
     assert abs(lg - le) <= 1e-6 * abs(le) and float((gg - ge).abs().max()) <= 1e-5 * float(ge.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parity AT the benchmarked sizes: the CTA-pair GEMMs, the persistent attention schedule
+# and the CUDA-graph slot at 128 ViT-L/14 cutouts, config 2 at its full 256 cutouts, outlier channels
+# ---------------------------------------------------------------------------------------------------------
+def test_vit_l14_128_cutouts_headline_size_matches_oracle(cuda_device):
+    """bench.py's headline shape: ViT-L/14, 128 cutouts in ONE launch sequence (M = 128 x 257 = 32 896 rows: CTA-pair
+    256 x 256 GEMM tiles, 148-CTA persistent schedules, 4096 attention work items), graph path on.
+
+    The CPU oracle cannot do 128 ViT-L/14 backward passes in seconds, so the batch is arranged for it: image 0 carries
+    8 cutouts, image 1 the other 120.  The gradient of image 0 depends only on its 8 cutouts, but they are computed
+    INSIDE the full-size launches; the oracle evaluates exactly that 8-cutout shard with the global scale."""
+    shape = SHAPES["ViT-L-14"]
+    sd = perturb(random_state_dict(shape, 0))
+    g = torch.Generator().manual_seed(21)
+    images = torch.rand(2, 3, 512, 512, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(0), 1, 512, 512, 128, 1.0, 128, 512)
+    rows[8:, 0] = 1  # the first 8 cutouts read image 0, the remaining 120 image 1
+    targets = torch.nn.functional.normalize(torch.randn(2, shape.embed, generator=g))
+    tw = torch.tensor([1.0, 0.5])
+    eng = GuidanceEngine(shape, sd, cuda_device, native.ACT_QUICKGELU)
+    assert eng.use_graphs
+    plan = eng.plan_cutouts(rows)
+    losses_seen, grads_seen = [], []
+    for _ in range(3):  # eager on the slot's buffers, capture, replay
+        img = images.to(cuda_device).requires_grad_()
+        loss = GuidanceLossFn.apply(img, eng, plan, targets.to(cuda_device), tw.to(cuda_device), 0.01, None)
+        loss.backward()
+        losses_seen.append(float(loss))
+        grads_seen.append(img.grad.detach().cpu())
+    assert eng._slot is not None and eng._slot.fwd_graph is not None and eng._slot.bwd_graph is not None
+    assert losses_seen[0] == losses_seen[1] == losses_seen[2], losses_seen
+    assert cosine(grads_seen[2], grads_seen[0]) >= 0.999999
+    # per-cutout encodings of the same 128-cutout batch (forward only) against the oracle on 12 of them
+    with torch.no_grad():
+        enc = EncodeImagesFn.apply(images.to(cuda_device), eng, plan, True).cpu()
+    pick = [0, 1, 2, 3, 7, 8, 9, 31, 64, 100, 126, 127]
+    enc_ref = guidance_oracle.encode_cutouts(images, rows[pick].tolist(), sd, shape.image_size, shape.patch,
+                                             shape.layers, shape.heads)
+    err = float((enc[pick] - enc_ref).norm(dim=1).max())
+    assert err <= 2e-2, f"per-cutout encodings differ by {err} (unit vectors)"
+    # the 8-cutout shard of image 0: loss share and image gradient
+    img_ref = images.clone().requires_grad_()
+    enc8 = guidance_oracle.encode_cutouts(img_ref, rows[:8].tolist(), sd, shape.image_size, shape.patch, shape.layers,
+                                          shape.heads)
+    dist = (enc8[:, None] - targets[None, :]).norm(dim=2).div(2).arcsin().square().mul(2)
+    share_ref = (dist * tw).sum() * 0.01 / (128 * 2)
+    share_ref.backward()
+    assert cosine(grads_seen[2][0], img_ref.grad[0]) >= GRAD_COS, cosine(grads_seen[2][0], img_ref.grad[0])
+    scale = float(grads_seen[2][0].norm() / img_ref.grad[0].norm())
+    assert abs(scale - 1.0) <= 2e-2, scale
+    # the loss of the whole batch from the native encodings vs the native loss (head + reduction at full size)
+    d_all = (enc[:, None] - targets[None, :]).norm(dim=2).div(2).arcsin().square().mul(2)
+    loss_from_enc = float((d_all * tw).sum() * 0.01 / (128 * 2))
+    assert abs(losses_seen[2] - loss_from_enc) <= 1e-3 * abs(loss_from_enc), (losses_seen[2], loss_from_enc)
+
+
+def test_config2_full_size_matches_oracle(cuda_device):
+    """BASELINE.json configs[1] at FULL size against the oracle (not against itself): ViT-B/32, 4 images of 512 x 512,
+    64 cutouts per image = 256 cutouts, loss and the whole [4,3,512,512] image gradient."""
+    shape = SHAPES["ViT-B-32"]
+    g = torch.Generator().manual_seed(2)
+    images = torch.rand(4, 3, 512, 512, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(0), 4, 512, 512, 64, 1.0, 64, 512)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    loss, loss_ref, grad, grad_ref, _ = run_case(cuda_device, shape, images, rows.tolist(), seed=5)
+    assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+    assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
+    for b in range(4):
+        assert cosine(grad[b], grad_ref[b]) >= GRAD_COS, (b, cosine(grad[b], grad_ref[b]))
+
+
+def outlier_state_dict(shape, seed, factor):
+    """Random-init weights with the outlier structure of trained CLIP towers: ~1 % of the LayerNorm gains and of the
+    c_fc rows (and their biases) scaled by `factor`, so a few residual-stream channels and MLP units carry values two
+    orders above the rest.  Exercises the bf16 residual-gradient stream and the tanh.approx QuickGELU."""
+    sd = perturb(random_state_dict(shape, seed))
+    g = torch.Generator().manual_seed(seed + 7)
+    for k in list(sd):
+        v = sd[k]
+        if (".ln_1.weight" in k or ".ln_2.weight" in k or k == "ln_pre.weight") and v.dim() == 1:
+            idx = torch.randperm(v.numel(), generator=g)[:max(1, v.numel() // 100)]
+            v = v.clone()
+            v[idx] *= factor
+            sd[k] = v
+        elif k.endswith("mlp.c_fc.weight"):
+            idx = torch.randperm(v.shape[0], generator=g)[:max(1, v.shape[0] // 100)]
+            v = v.clone()
+            v[idx] *= factor
+            sd[k] = v
+    return sd
+
+
+@pytest.mark.parametrize("factor", [30.0, 100.0])
+def test_outlier_channels_match_oracle(cuda_device, factor):
+    """Every parity case above uses benign random-init weights; trained CLIP has outlier channels."""
+    shape = SHAPES["ViT-B-32"]
+    sd = outlier_state_dict(shape, 3, factor)
+    g = torch.Generator().manual_seed(31)
+    images = torch.rand(1, 3, 224, 256, generator=g)
+    rows = cutouts.sample_cutouts(torch.Generator().manual_seed(9), 1, 224, 256, 6, 1.0, 64, 224).tolist()
+    targets = torch.nn.functional.normalize(torch.randn(2, shape.embed, generator=g))
+    tw = torch.ones(2)
+    img_ref = images.clone().requires_grad_()
+    loss_ref = guidance_oracle.guidance_loss(img_ref, rows, sd, shape.image_size, shape.patch, shape.layers, shape.heads,
+                                             targets, tw, 1.0)
+    loss_ref.backward()
+    eng = GuidanceEngine(shape, sd, cuda_device, native.ACT_QUICKGELU)
+    img = images.to(cuda_device).requires_grad_()
+    loss = GuidanceLossFn.apply(img, eng, eng.plan_cutouts(np.asarray(rows, dtype=np.int32)), targets.to(cuda_device),
+                                tw.to(cuda_device), 1.0, None)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_RTOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    assert cosine(img.grad.cpu(), img_ref.grad) >= GRAD_COS, cosine(img.grad.cpu(), img_ref.grad)
+
+
+def test_two_configurations_interleaved_after_capture(cuda_device):
+    """two loss modules with different cutout counts share one memoised encoder (one engine, one graph
+    slot).  After A's graphs are captured, a step that evaluates A and B before either backward must not let B free or
+    overwrite anything A's pending backward replays against (the slot owns its workspace; a busy slot is kept and the
+    other configuration runs eagerly)."""
+    a = losses.CLIP("ViT-B-32", n_cutouts=6, min_size=64, seed=1, weights_seed=11)
+    b = losses.CLIP("ViT-B-32", n_cutouts=20, min_size=64, seed=2, weights_seed=11)
+    assert a.model is b.model
+    g = torch.Generator().manual_seed(0)
+    enc = torch.randn(2, 512, generator=g)
+    a.add_encodings_(enc)
+    b.add_encodings_(enc)
+    images = torch.rand(1, 3, 192, 192, generator=g).to(cuda_device)
+
+    def grads_separately(mod, seed):
+        mod.generator.manual_seed(seed)
+        img = images.clone().requires_grad_()
+        mod(img).backward()
+        return img.grad.clone()
+
+    gb = grads_separately(b, 8)
+    for s in range(3):  # A alone: eager, capture, replay
+        grads_separately(a, 100 + s)
+    eng = a.model.engine()
+    assert eng._slot is not None and eng._slot.bwd_graph is not None
+    ga = grads_separately(a, 7)
+    slot_a = eng._slot
+    for _ in range(2):
+        a.generator.manual_seed(7)
+        b.generator.manual_seed(8)
+        img = images.clone().requires_grad_()
+        la = a(img)   # A's slot is now busy ...
+        lb = b(img)   # ... so B (more cutouts: larger workspace) must neither replace the slot nor touch its buffers
+        (la + lb).backward()
+        assert cosine(img.grad, ga + gb) >= 0.999999, cosine(img.grad, ga + gb)
+        assert float((img.grad - (ga + gb)).abs().max()) <= 1e-5 * float((ga + gb).abs().max()) + 1e-12
+        assert eng._slot is slot_a, "the busy slot (captured graphs of A) must survive B's call"
+
+
+def test_cutout_rows_outside_the_image_raise(cuda_device):
+    """caller-supplied rows are validated on the host (the kernels index and scatter-add straight from them)."""
+    from perceptor_b200 import models
+    model = models.CLIP("ViT-B-32", seed=11)
+    images = torch.rand(2, 3, 96, 80, device=cuda_device)
+    ok = model.encode_images(images, cutout_rows=np.array([[0, 0, 0, 80], [1, 16, 0, 64]]))
+    assert ok.shape == (2, 512)
+    for bad in ([[2, 0, 0, 32]], [[0, 40, 0, 64]], [[0, 0, 30, 64]], [[-1, 0, 0, 32]], [[0, 0, 0, 0]]):
+        with pytest.raises(ValueError):
+            model.encode_images(images, cutout_rows=np.array(bad))
+    eng = model.engine()
+    with pytest.raises(ValueError):
+        GuidanceLossFn.apply(images.clone().requires_grad_(), eng, eng.plan_cutouts(np.array([[0, 90, 0, 32]], dtype=np.int32)),
+                             torch.randn(1, 512, device=cuda_device), torch.ones(1, device=cuda_device), 1.0, None)
