@@ -6,10 +6,10 @@
 
 Beside the hot path (losses, models, cutouts, resize_tables, vit, guidance, native) the package carries the callers'
 glue it was widened into: velocity_diffusion (Predictions, schedule_ts, guided_step), transforms
-(clamp_with_grad), utils (gradient_checkpoint), text (CLIP tokenizer + text tower) and checkpoints (OpenAI /
+(clamp_with_grad), text (CLIP tokenizer + text tower) and checkpoints (OpenAI /
 open_clip / Hugging Face state-dict ingestion).
 """
-from . import checkpoints, cutouts, losses, models, resize_tables, text, transforms, utils, velocity_diffusion, vit  # noqa: F401
+from . import checkpoints, cutouts, losses, models, resize_tables, text, transforms, velocity_diffusion, vit  # noqa: F401
 
-__all__ = ["losses", "models", "cutouts", "resize_tables", "vit", "velocity_diffusion", "transforms", "utils", "text",
+__all__ = ["losses", "models", "cutouts", "resize_tables", "vit", "velocity_diffusion", "transforms", "text",
            "checkpoints"]

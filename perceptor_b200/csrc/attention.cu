@@ -584,14 +584,8 @@ int attn_delta(const void* out, const void* d_out, float* delta, int n, int T, i
 int attn_bwd_legacy(const void* qkv, const void* d_out, const float* lse, const float* delta, void* d_qkv, int n, int T,
                     int heads, int begin, cudaStream_t s) {
     if (begin >= T) return 0;
-    static bool configured = false;
-    if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(sizeof(BwdSmem))));
-        PCG_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(sizeof(BwdSmem))));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BwdSmem)))); PCG_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BwdSmem)))));
     const dim3 grid(ceil_div(T - begin, kTile), heads, n);
     attn_bwd_dkdv_kernel<<<grid, 128, sizeof(BwdSmem), s>>>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(d_out),
                                                            lse, delta, static_cast<bf16*>(d_qkv), T, heads, begin);

@@ -2234,11 +2234,8 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     if (!g_force_legacy && use_pack(T, heads)) {
         CUtensorMap pmap;
         if (int rc = make_map3(&pmap, qkv, n, T, 3 * D, 64)) return rc;
-        static bool pack_configured = false;
-        if (!pack_configured) {
-            PCG_CUDA(cudaFuncSetAttribute(attn_fwd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackFwdSmem));
-            pack_configured = true;
-        }
+        static PerDeviceOnce pack_configured;
+        PCG_ONCE_PER_DEVICE(pack_configured, PCG_CUDA(cudaFuncSetAttribute(attn_fwd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackFwdSmem)));
         PackParams pp{T, heads, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, nullptr, nullptr, nullptr};
         attn_fwd_pack_kernel<<<dim3(heads / 2, n), kPackFwdThreads, kPackFwdSmem, s>>>(pmap, pp);
         PCG_LAUNCH_CHECK("attn_fwd_pack_kernel");
@@ -2248,11 +2245,8 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     CUtensorMap map;
     if (int rc = make_map3(&map, qkv, n, T, 3 * D)) return rc;
     if (use_flash_fwd(T)) {
-        static bool flash_configured = false;
-        if (!flash_configured) {
-            PCG_CUDA(cudaFuncSetAttribute(attn_fwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlashSmemBytes));
-            flash_configured = true;
-        }
+        static PerDeviceOnce flash_configured;
+        PCG_ONCE_PER_DEVICE(flash_configured, PCG_CUDA(cudaFuncSetAttribute(attn_fwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlashSmemBytes)));
         FwdParams pf{T, heads, T, (T + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
                      nullptr, 2 * sm_count(), g_fwd_stagger};
         attn_fwd_flash_kernel<<<dim3((T + 127) / 128, heads, n), kFwdThreads, kFlashSmemBytes, s>>>(map, pf);
@@ -2261,7 +2255,8 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
     }
     const int nv = T - 1;
     if (g_fwd_persist) {
-        PCG_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2SmemBytes));
+        static PerDeviceOnce persist_configured;
+        PCG_ONCE_PER_DEVICE(persist_configured, PCG_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2SmemBytes)));
         const int tiles = (nv + 127) / 128;
         const long long items = static_cast<long long>(n) * heads * tiles;
         PCG_CHECK_ARG(items < (1ll << 30), "pcg_attn_fwd: too many (cutout, head, tile) items");
@@ -2272,7 +2267,8 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
         PCG_LAUNCH_CHECK("attn_fwd_persist_kernel");
         return 0;
     }
-    PCG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    static PerDeviceOnce configured;
+    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes)));
     FwdParams p{T, heads, nv, (nv + 15) & ~15, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse,
                 g_trace, 2 * sm_count(), g_fwd_stagger};
     attn_fwd_tc_kernel<<<dim3((nv + 127) / 128, heads, n), kFwdThreads, kFwdSmemBytes, s>>>(map, p);
@@ -2299,11 +2295,8 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
         CUtensorMap pmap, pmap_do;
         if (int rc = make_map3(&pmap, qkv, n, T, 3 * D, 64)) return rc;
         if (int rc = make_map3(&pmap_do, d_out, n, T, D, 64)) return rc;
-        static bool pack_configured = false;
-        if (!pack_configured) {
-            PCG_CUDA(cudaFuncSetAttribute(attn_bwd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackBwdSmem));
-            pack_configured = true;
-        }
+        static PerDeviceOnce pack_configured;
+        PCG_ONCE_PER_DEVICE(pack_configured, PCG_CUDA(cudaFuncSetAttribute(attn_bwd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackBwdSmem)));
         if (int rc = attn_delta(out, d_out, delta_ws, n, T, heads, s)) return rc;
         PackParams pp{T, heads, static_cast<const bf16*>(qkv), nullptr, const_cast<float*>(lse),
                       static_cast<const bf16*>(d_out), delta_ws, static_cast<bf16*>(d_qkv)};
@@ -2315,11 +2308,8 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
         CUtensorMap lmap, lmap_do;
         if (int rc = make_map3(&lmap, qkv, n, T, 3 * D)) return rc;
         if (int rc = make_map3(&lmap_do, d_out, n, T, D)) return rc;
-        static bool long_configured = false;
-        if (!long_configured) {
-            PCG_CUDA(cudaFuncSetAttribute(attn_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongSmemBytes));
-            long_configured = true;
-        }
+        static PerDeviceOnce long_configured;
+        PCG_ONCE_PER_DEVICE(long_configured, PCG_CUDA(cudaFuncSetAttribute(attn_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongSmemBytes)));
         if (int rc = attn_delta(out, d_out, delta_ws, n, T, heads, s)) return rc;
         float* dq_ws = delta_ws + bwd_delta_floats(n, T, heads);
         const size_t rows = static_cast<size_t>(n) * T;
@@ -2340,11 +2330,8 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
     CUtensorMap map, map_do;
     if (int rc = make_map3(&map, qkv, n, T, 3 * D)) return rc;
     if (int rc = make_map3(&map_do, d_out, n, T, D)) return rc;
-    static bool configured = false;
-    if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes)));
     const int nv = T - 1;
     BwdParams p{T,   heads, nv, (nv + 127) / 128, static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
                 static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace, sm_count(), g_bwd_stagger};  // delta: in-kernel

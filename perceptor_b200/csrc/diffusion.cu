@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) clamp_grad_kernel(const float* __res
     for (size_t i = blockIdx.x * static_cast<size_t>(kThreads) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * kThreads) {
         const float xv = x[i];
-        const float cl = fminf(fmaxf(xv, lo), hi);
+        const float cl = (xv != xv) ? xv : fminf(fmaxf(xv, lo), hi);  // NaN propagates like torch.clamp (fminf / fmaxf drop it)
         if (kMode == 0) {
             out[i] = cl;
         } else {

@@ -415,12 +415,8 @@ bool g_pdl_enabled = []() {
 template <int BN, int MODE, int ACT, int CTAS>
 int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
     using Cfg = TileCfg<BN, CTAS>;
-    static bool configured = false;
-    if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)));
     const int tiles = ceil_div(p.M, BM * CTAS) * ceil_div(p.N, BN);
     const int slots = sm_count() / CTAS;  // clusters (or CTAs) that run concurrently
     const int grid = (tiles < slots ? tiles : slots) * CTAS;

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/pcg.h"
 
 namespace pcg {
@@ -49,6 +51,24 @@ struct ProfileScope {
     ProfileScope(int kind, double work, cudaStream_t stream) : s(stream) { profile_begin(kind, work, stream); }
     ~ProfileScope() { profile_end(s); }
 };
+
+// One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device property: an encoder moved to a second GPU of the
+// same process must configure its kernels there too), safe against concurrent first calls (autograd runs backward on
+// its own thread).  `static PerDeviceOnce once; PCG_TRY_ONCE(once, cudaFuncSetAttribute(...));`
+struct PerDeviceOnce {
+    std::mutex mu;
+    uint64_t done = 0;  // bit d: device ordinal d is configured (ordinals >= 64 are configured every time)
+};
+#define PCG_ONCE_PER_DEVICE(once, ...)                                          \
+    do {                                                                        \
+        int _dev = 0;                                                           \
+        PCG_CUDA(cudaGetDevice(&_dev));                                         \
+        std::lock_guard<std::mutex> _lock((once).mu);                           \
+        if (_dev >= 64 || !(((once).done >> _dev) & 1ull)) {                    \
+            __VA_ARGS__;                                                        \
+            if (_dev < 64) (once).done |= 1ull << _dev;                         \
+        }                                                                       \
+    } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

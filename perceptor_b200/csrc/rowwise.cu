@@ -343,7 +343,7 @@ __device__ __forceinline__ void combine_parts(float* base, int n_rows, int width
 // an upstream gradient d_enc through the normalisation)
 __global__ void __launch_bounds__(kHeadThreads)
 head_dist_kernel(float* __restrict__ z, const float* __restrict__ targets, const float* __restrict__ tweights,
-                 int E, int M, float scale, int normalize, float* __restrict__ loss_sum, float* __restrict__ enc_out,
+                 int E, int M, float scale, int normalize, float* __restrict__ loss_part, float* __restrict__ enc_out,
                  const float* __restrict__ d_enc, float* __restrict__ dz) {
     extern __shared__ float sm[];
     float* ebuf = sm;      // [E]
@@ -375,16 +375,23 @@ head_dist_kernel(float* __restrict__ z, const float* __restrict__ targets, const
         }
         rr = block_sum(rr, red);
         const float r = sqrtf(rr);
-        const float half = fminf(0.5f * r, 1.0f);
+        // r / 2 > 1 cannot happen between unit vectors; it does when a caller stores un-normalised targets (OpenCLIP
+        // keeps them as given, perceptor/losses/open_clip.py:58-85).  The reference then returns NaN (asin of > 1)
+        // and so does this: a finite loss with an exploding gradient would hide the mistake.  Rounding slop just
+        // above 1 (antipodal unit vectors) is treated as exactly 1.
+        const float half_raw = 0.5f * r;
+        const float half = !(half_raw <= 1.000001f) ? __int_as_float(0x7fc00000) : fminf(half_raw, 1.0f);  // NaN in, NaN out
         const float theta = asinf(half);
         const float w = tweights[m];
         loss_local += w * 2.0f * theta * theta;
-        // d/de = 2*theta / sqrt(1 - r^2/4) * (e - t) / r ; subgradient 0 at r == 0 (torch.norm backward)
-        const float denom = sqrtf(fmaxf(1.0f - half * half, 1e-12f)) * r;
-        const float coef = (r > 0.f) ? w * 2.0f * theta / denom : 0.f;
+        // d/de = 2*theta / sqrt(1 - r^2/4) * (e - t) / r ; subgradient 0 at r == 0 (torch.norm backward) and at the
+        // antipode r == 2, where the derivative of asin is unbounded
+        const float one_minus = 1.0f - half * half;
+        const float coef = (r == 0.f || one_minus <= 1e-12f) ? 0.f : w * 2.0f * theta / (sqrtf(one_minus) * r);
         for (int e = tid; e < E; e += kHeadThreads) gbuf[e] += coef * (ebuf[e] - tm[e]);
     }
-    if (tid == 0 && loss_sum != nullptr && M > 0) atomicAdd(loss_sum, loss_local * scale);
+    // per-cutout partial; head_loss_sum_kernel adds them in a fixed order (bit-reproducible, unlike atomics)
+    if (tid == 0 && loss_part != nullptr) loss_part[n] = loss_local * scale;
     if (dz == nullptr) return;
     __syncthreads();
     // through F.normalize: dz = (de - e (e . de)) / |z|
@@ -395,6 +402,17 @@ head_dist_kernel(float* __restrict__ z, const float* __restrict__ targets, const
     }
     for (int e = tid; e < E; e += kHeadThreads)
         dz[static_cast<size_t>(n) * E + e] = normalize ? (gbuf[e] - ebuf[e] * dot) * inv_norm * scale : gbuf[e] * scale;
+}
+
+// *loss_sum += sum_n loss_part[n], always in the same order: thread t adds elements t, t + 256, ... sequentially, then
+// the block tree-reduces
+__global__ void __launch_bounds__(kHeadThreads) head_loss_sum_kernel(const float* __restrict__ loss_part, int n,
+                                                                     float* __restrict__ loss_sum) {
+    __shared__ float red[kHeadThreads / 32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += kHeadThreads) s += loss_part[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *loss_sum += s;
 }
 
 // dx[CLS row] = ln_post'(dy): statistics recomputed from x (one 4 KB row)
@@ -501,8 +519,8 @@ extern "C" int pcg_embed_bwd(const float* dx0, const void* dx0_bf16, const float
 
 extern "C" size_t pcg_head_workspace_bytes(int n, int D, int E) {
     if (n <= 0 || D <= 0 || E <= 0) return 0;
-    // y [n,D], dy [parts][n,D], z [parts][n,E], dz [n,E]
-    return (static_cast<size_t>(n) * D * (1 + kHgParts) + static_cast<size_t>(n) * E * (1 + kHgParts)) * sizeof(float);
+    // y [n,D], dy [parts][n,D], z [parts][n,E], dz [n,E], per-cutout loss partials [n]
+    return (static_cast<size_t>(n) * D * (1 + kHgParts) + static_cast<size_t>(n) * E * (1 + kHgParts) + n) * sizeof(float);
 }
 
 extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_b, const float* proj,
@@ -522,6 +540,7 @@ extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_
     float* dy = y + static_cast<size_t>(n) * D;                  // [parts][n, D]
     float* z = dy + static_cast<size_t>(n) * D * kHgParts;       // [parts][n, E]
     float* dz = z + static_cast<size_t>(n) * E * kHgParts;       // [n, E]
+    float* loss_part = dz + static_cast<size_t>(n) * E;          // [n]
     if (dx != nullptr) PCG_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(n) * T * D * sizeof(float), s));
     if (dx_bf16 != nullptr) PCG_CUDA(cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(n) * T * D * 2, s));
     head_ln_kernel<<<n, kHeadThreads, 0, s>>>(x, ln_g, ln_b, T, D, y);
@@ -531,8 +550,13 @@ extern "C" int pcg_head_loss(const float* x, const float* ln_g, const float* ln_
     const bool has_loss = targets != nullptr && M > 0;
     if (!has_loss && d_enc == nullptr && enc_out == nullptr) return 0;
     head_dist_kernel<<<n, kHeadThreads, smem, s>>>(z, has_loss ? targets : nullptr, tweights, E, has_loss ? M : 0, scale,
-                                                   normalize, loss_sum, enc_out, d_enc, want_dx ? dz : nullptr);
+                                                   normalize, (has_loss && loss_sum) ? loss_part : nullptr, enc_out, d_enc,
+                                                   want_dx ? dz : nullptr);
     PCG_LAUNCH_CHECK("head_dist_kernel");
+    if (has_loss && loss_sum != nullptr) {
+        head_loss_sum_kernel<<<1, kHeadThreads, 0, s>>>(loss_part, n, loss_sum);
+        PCG_LAUNCH_CHECK("head_loss_sum_kernel");
+    }
     if (!want_dx) return 0;
     head_gemm_kernel<true><<<dim3(ceil_div(D, kHgCols), ceil_div(n, kHgRows), kHgParts), kHeadThreads, 0, s>>>(dz, proj, dy, n, D, E);
     PCG_LAUNCH_CHECK("head_gemm_kernel");

@@ -420,12 +420,8 @@ extern "C" int pcg_sampler_fwd(const float* images, int B, int H, int W, const i
     PCG_CHECK_ARG(patches_bf16 == nullptr || kpad >= 3 * patch * patch, "pcg_sampler_fwd: kpad %d < 3*p*p", kpad);
     SamplerParams p;
     fill_params(p, images, B, H, W, cuts, tabs, R, patch, kpad, mean_host, std_host);
-    static bool configured = false;
-    if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(sampler_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        PCG_CUDA(cudaFuncSetAttribute(sampler_fwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(sampler_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); PCG_CUDA(cudaFuncSetAttribute(sampler_fwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)));
     ProfileScope prof(PCG_PROF_SAMPLER_FWD, 6.0 * n_cut * R * R, static_cast<cudaStream_t>(stream));
     if (!g_force_scalar && vec_ok(images, W, R, patch)) {
         p.RS = vec_row_stride(max_in_w);
@@ -461,12 +457,8 @@ extern "C" int pcg_sampler_bwd(const void* d_patches_bf16, const float* d_out_f3
                   "pcg_sampler_bwd: bad shape n_cut=%d R=%d patch=%d max_in_w=%d", n_cut, R, patch, max_in_w);
     SamplerParams p;
     fill_params(p, nullptr, B, H, W, cuts, tabs, R, patch, kpad, nullptr, std_host);
-    static bool configured = false;
-    if (!configured) {
-        PCG_CUDA(cudaFuncSetAttribute(sampler_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        PCG_CUDA(cudaFuncSetAttribute(sampler_bwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(sampler_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); PCG_CUDA(cudaFuncSetAttribute(sampler_bwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)));
     ProfileScope prof(PCG_PROF_SAMPLER_BWD, 6.0 * n_cut * R * R, static_cast<cudaStream_t>(stream));
     if (!g_force_scalar && vec_ok(d_images, W, R, patch) &&
         (d_out_f32 == nullptr || (reinterpret_cast<uintptr_t>(d_out_f32) & 7u) == 0)) {

@@ -12,8 +12,9 @@ def _launch(x, g, lo, hi):
     if not x.is_cuda:
         raise RuntimeError("the native clamp_with_grad needs CUDA tensors; there is no CPU fallback")
     out = torch.empty_like(x)
-    native.check(native.lib().pcg_clamp_with_grad(native.ptr(x), native.ptr(g), native.ptr(out), x.numel(), float(lo),
-                                                  float(hi), native.stream_ptr()), "pcg_clamp_with_grad")
+    with torch.cuda.device(x.device):  # launch on the tensor's GPU and ITS current stream
+        native.check(native.lib().pcg_clamp_with_grad(native.ptr(x), native.ptr(g), native.ptr(out), x.numel(), float(lo),
+                                                      float(hi), native.stream_ptr()), "pcg_clamp_with_grad")
     return out
 
 
@@ -21,14 +22,15 @@ class ClampWithGradFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, min=0, max=1):
         ctx.min, ctx.max = float(min), float(max)
+        ctx.dtype = input.dtype  # fp32 kernel; half / bf16 inputs get their dtype back (the reference preserves it)
         input = input.contiguous().float()
         ctx.save_for_backward(input)
-        return _launch(input, None, ctx.min, ctx.max)
+        return _launch(input, None, ctx.min, ctx.max).to(ctx.dtype)
 
     @staticmethod
     def backward(ctx, grad_in):
         (input,) = ctx.saved_tensors
-        return _launch(input, grad_in.contiguous().float(), ctx.min, ctx.max), None, None
+        return _launch(input, grad_in.contiguous().float(), ctx.min, ctx.max).to(ctx.dtype), None, None
 
 
 def clamp_with_grad(tensor, min=0.0, max=1.0):

@@ -85,15 +85,17 @@ def _coef(device, *rows) -> torch.Tensor:
 def _launch_affine(x, y, coef, limit):
     if not x.is_cuda:
         raise RuntimeError("the native guided-sampling path needs CUDA tensors; there is no CPU fallback")
+    dtype = x.dtype  # the kernel computes in fp32; the result goes back to the caller's dtype like the reference's torch ops
     x = x.contiguous().float()
     y = None if y is None else y.contiguous().float()
     out = torch.empty_like(x)
     n = coef.shape[1]
     if x.shape[0] != n:
         raise ValueError(f"batch {x.shape[0]} does not match {n} timesteps")
-    native.check(native.lib().pcg_affine2(native.ptr(x), native.ptr(y), native.ptr(coef), native.ptr(out), n,
-                                          x.numel() // n, float(limit), native.stream_ptr()), "pcg_affine2")
-    return out
+    with torch.cuda.device(x.device):  # launch on the tensor's GPU and ITS current stream, not the process default
+        native.check(native.lib().pcg_affine2(native.ptr(x), native.ptr(y), native.ptr(coef), native.ptr(out), n,
+                                              x.numel() // n, float(limit), native.stream_ptr()), "pcg_affine2")
+    return out if dtype == torch.float32 or not dtype.is_floating_point else out.to(dtype)
 
 
 class _Affine2(torch.autograd.Function):

@@ -301,6 +301,29 @@ def test_head_loss_edge_cases(cuda_device):
         assert torch.isfinite(loss).all() and torch.isfinite(dx).all()
     loss0, _, dx0, _ = ops.head_loss(x[: t], ln_g, ln_b, proj, enc[:1].clone(), torch.ones(1, device=cuda_device), 1, t, 1.0)
     assert float(loss0) < 1e-6 and float(dx0.abs().max()) < 1e-3
+    # an un-normalised target further than 2 away: the reference's asin(r / 2 > 1) is NaN, and so is this
+    far = 3.0 * enc[:1].clone()
+    loss_far, _, dx_far, _ = ops.head_loss(x, ln_g, ln_b, proj, -far, torch.ones(1, device=cuda_device), n, t, 1.0)
+    ref_far = (enc[:, None] - (-far)[None, :]).norm(dim=2).div(2).arcsin().square().mul(2).sum()
+    assert torch.isnan(ref_far) and torch.isnan(loss_far).all() and torch.isnan(dx_far).any()
+
+
+def test_head_loss_is_bit_reproducible(cuda_device):
+    """The loss is summed over cutouts in a fixed order (per-cutout partials + one reducing CTA), not with atomics."""
+    n, t, d, e, m = 128, 3, 256, 64, 2
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(n * t, d, generator=g).to(cuda_device)
+    ln_g, ln_b = torch.ones(d, device=cuda_device), torch.zeros(d, device=cuda_device)
+    proj = (torch.randn(d, e, generator=g) * d**-0.5).to(cuda_device)
+    targets = torch.nn.functional.normalize(torch.randn(m, e, generator=g)).to(cuda_device)
+    tw = torch.ones(m, device=cuda_device)
+    first = None
+    for _ in range(6):
+        loss, _, dx, _ = ops.head_loss(x, ln_g, ln_b, proj, targets, tw, n, t, 1.0 / (n * m))
+        cur = (float(loss), dx.clone())
+        if first is None:
+            first = cur
+        assert cur[0] == first[0] and torch.equal(cur[1], first[1])
 
 
 # ------------------------------------------------------------------------------------------------ sampler

@@ -117,3 +117,22 @@ def test_guided_step_matches_oracle_composition(cuda_device):
     d, dr = (nxt.cpu() - dz.step(images, ts, velocities, to_ts)).double().flatten(), \
         (nxt_ref - dz.step(images, ts, velocities, to_ts)).double().flatten()
     assert float(d @ dr / (d.norm() * dr.norm())) >= 0.999  # the guidance displacement, bf16 path vs fp32 oracle
+
+
+def test_clamp_with_grad_dtype_and_nan(cuda_device):
+    """half inputs keep their dtype (the reference's torch ops do) and NaN propagates like torch.clamp."""
+    from perceptor_b200 import transforms
+    x = torch.tensor([-0.5, 0.25, 1.5, float("nan")], device=cuda_device)
+    y = transforms.clamp_with_grad(x, 0.0, 1.0)
+    assert torch.equal(y[:3], torch.tensor([0.0, 0.25, 1.0], device=cuda_device)) and torch.isnan(y[3])
+    for dt in (torch.float16, torch.bfloat16):
+        xh = torch.tensor([-0.5, 0.25, 1.5], device=cuda_device, dtype=dt).requires_grad_()
+        yh = transforms.clamp_with_grad(xh, 0.0, 1.0)
+        assert yh.dtype == dt and torch.equal(yh.detach().float(), torch.tensor([0.0, 0.25, 1.0], device=cuda_device))
+        yh.sum().backward()
+        assert xh.grad.dtype == dt
+        # reference rule (clamp_with_grad.py:19-27): grad * [grad * (x - clamp(x)) >= 0] with grad = +1
+        assert torch.equal(xh.grad.float(), torch.tensor([0.0, 1.0, 1.0], device=cuda_device))
+    p = vd.Predictions(torch.rand(2, 3, 8, 8, device=cuda_device).half(), torch.tensor([0.3, 0.6]),
+                       torch.randn(2, 3, 8, 8, device=cuda_device).half())
+    assert p.denoised_images.dtype == torch.float16
