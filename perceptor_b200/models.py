@@ -7,6 +7,7 @@ are no pretrained weights, so weights are random-init unless a `state_dict` is s
 """
 from __future__ import annotations
 
+import dataclasses
 import warnings
 import weakref
 
@@ -162,3 +163,66 @@ def CLIP(architecture: str, precision=None, **kwargs):
 
 def normalize_encodings(encodings: torch.Tensor) -> torch.Tensor:
     return F.normalize(encodings)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# TransformersOpenAICLIP surface (perceptor/models/transformers_openai_clip.py:17-137): the same
+# encoders addressed by Hugging Face model id, `encode_images` / `encode_texts` returning an `Encodings` record.
+# ---------------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Encodings:
+    """perceptor/models/transformers_openai_clip.py:17-21.  `features` (HF's BaseModelOutputWithPooling with every hidden
+    state) is not produced by the native path: the engine keeps activations in its own stash layout, so it is None."""
+    features: object
+    unnormalized_encodings: torch.Tensor
+    encodings: torch.Tensor
+
+
+# Hugging Face id -> (architecture, weights) of the towers this package builds (perceptor/models/
+# transformers_openai_clip.py:36-50 lists more: the XLM-Roberta / sentence-transformers text towers are out of scope)
+_HF_IDS = {
+    "openai/clip-vit-base-patch32": ("ViT-B-32-quickgelu", "openai"),
+    "openai/clip-vit-base-patch16": ("ViT-B-16", "openai"),
+    "openai/clip-vit-large-patch14": ("ViT-L-14", "openai"),
+    "openai/clip-vit-large-patch14-336": ("ViT-L-14-336", "openai"),
+    "laion/CLIP-ViT-L-14-laion2B-s32B-b82K": ("ViT-L-14", "laion2b_s32b_b82k"),
+    "laion/CLIP-ViT-B-32-laion2B-s34B-b79K": ("ViT-B-32", "laion2b_s34b_b79k"),
+    "laion/CLIP-ViT-H-14-laion2B-s32B-b79K": ("ViT-H-14", "laion2b_s32b_b79k"),
+    "laion/CLIP-ViT-g-14-laion2B-s12B-b42K": ("ViT-g-14", "laion2b_s12b_b42k"),
+}
+
+
+class TransformersOpenAICLIP(torch.nn.Module):
+    """`TransformersOpenAICLIP(name)` of the reference with the native image tower behind it.  There is no network here:
+    pass the checkpoint as `state_dict=` (Hugging Face, open_clip or OpenAI layout; `checkpoints.normalize_state_dict`)
+    or get random-init weights.  `bfloat16` is accepted for signature parity; the native path is bf16 either way."""
+
+    def __init__(self, name="openai/clip-vit-large-patch14", bfloat16=True, *, state_dict=None, seed=0, bpe_path=None):
+        super().__init__()
+        if name not in _HF_IDS:
+            raise ValueError(f"Invalid model id: {name} (known: {sorted(_HF_IDS)})")
+        self.name = name
+        architecture, weights = _HF_IDS[name]
+        self.clip = OpenCLIP(architecture, weights, "bf16", state_dict=state_dict, seed=seed, bpe_path=bpe_path)
+        # (the reference takes 224 from the base-patch32 feature extractor for every id, :71-75; the native tower's
+        # positional embedding fixes the size, so the 336 model resizes to 336 here)
+        self.image_size = list(self.clip.image_size)
+
+    @property
+    def device(self):
+        return self.clip.device
+
+    def encode_images(self, images) -> Encodings:
+        unnormalized = self.clip.encode_images(images, normalize=False)
+        return Encodings(None, unnormalized, unnormalized / unnormalized.norm(p=2, dim=-1, keepdim=True))
+
+    def encode_texts(self, texts) -> Encodings:
+        unnormalized = self.clip.encode_texts(texts, normalize=False)
+        return Encodings(None, unnormalized, unnormalized / unnormalized.norm(p=2, dim=-1, keepdim=True))
+
+    @staticmethod
+    def spherical_distance(encodings_a: Encodings, encodings_b: Encodings) -> torch.Tensor:
+        return (encodings_a.encodings[:, None] - encodings_b.encodings[None, :]).norm(dim=2).div(2).arcsin().square().mul(2)
+
+    def forward(self, _):
+        raise NotImplementedError

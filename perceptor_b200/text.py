@@ -9,8 +9,9 @@ Mirrors
     `ftfy.fix_text` call of basic_clean (:60-63) is applied only when ftfy is importable.
   * the text transformer restated at perceptor/models/ruclip/model.py:165-228: token + positional embedding ->
     pre-LN residual attention blocks under a causal mask -> ln_final -> the end-of-text position @ text_projection.
-The merge table (`bpe_simple_vocab_16e6.txt.gz`, 1.3 MB) is data the user supplies: pass `bpe_path=` or set
-PCG_BPE_VOCAB; it is not vendored.
+The merge table (`bpe_simple_vocab_16e6.txt.gz`, 1.3 MB: OpenAI CLIP's published vocabulary, MIT licence) ships as
+package data (perceptor_b200/data/, see its README) so that `add_texts_` works out of the box; `bpe_path=` or
+PCG_BPE_VOCAB select another table.
 """
 from __future__ import annotations
 
@@ -29,6 +30,7 @@ try:  # pragma: no cover - optional dependency of the reference's basic_clean
 except ImportError:  # pragma: no cover
     ftfy = None
 
+DEFAULT_VOCAB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "bpe_simple_vocab_16e6.txt.gz")
 SOT, EOT = "<|startoftext|>", "<|endoftext|>"
 N_MERGES = 49152 - 256 - 2
 _PATTERN = re.compile(r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""",
@@ -53,11 +55,12 @@ def byte_alphabet() -> dict[int, str]:
 
 class SimpleTokenizer:
     def __init__(self, bpe_path: str | os.PathLike | None = None):
-        bpe_path = bpe_path or os.environ.get("PCG_BPE_VOCAB")
-        if not bpe_path or not os.path.exists(bpe_path):
+        bpe_path = bpe_path or os.environ.get("PCG_BPE_VOCAB") or DEFAULT_VOCAB
+        if not os.path.exists(bpe_path):
             raise FileNotFoundError(
-                "the CLIP BPE merge table (bpe_simple_vocab_16e6.txt.gz) is not vendored: pass bpe_path= or set "
-                "PCG_BPE_VOCAB, or add precomputed encodings with add_encodings_()")
+                f"the CLIP BPE merge table {bpe_path} does not exist: pass bpe_path= or set PCG_BPE_VOCAB (the packaged "
+                "copy is perceptor_b200/data/bpe_simple_vocab_16e6.txt.gz), or add precomputed encodings with "
+                "add_encodings_()")
         opener = gzip.open if str(bpe_path).endswith(".gz") else open
         with opener(bpe_path, "rb") as f:
             lines = f.read().decode("utf-8").split("\n")

@@ -11,8 +11,7 @@ import torch
 from perceptor_b200 import checkpoints, text
 
 GOLDEN = Path(__file__).parent / "golden"
-REF_VOCAB = Path("/root/reference/perceptor/models/glide_clip/bpe_simple_vocab_16e6.txt.gz")
-VOCAB = Path(os.environ.get("PCG_BPE_VOCAB", REF_VOCAB))
+VOCAB = Path(os.environ.get("PCG_BPE_VOCAB", text.DEFAULT_VOCAB))  # the packaged table (perceptor_b200/data/)
 
 
 def test_byte_alphabet_is_the_gpt2_table():
@@ -46,7 +45,6 @@ def test_bpe_merges_lowest_rank_first_on_a_toy_table(tmp_path):
         text.SimpleTokenizer(tmp_path / "missing.gz")
 
 
-@pytest.mark.skipif(not VOCAB.exists(), reason="CLIP merge table not available (it is not vendored)")
 def test_token_ids_match_the_reference_tokenizer():
     z = json.loads((GOLDEN / "text_tokens.json").read_text())
     tok = text.SimpleTokenizer(VOCAB)
