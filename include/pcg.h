@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PCG_ABI_VERSION 2
+#define PCG_ABI_VERSION 3
 
 enum { PCG_ACT_QUICKGELU = 0, PCG_ACT_GELU = 1 };
 
@@ -45,17 +45,25 @@ typedef struct pcg_vit_config {
     int32_t tokens;     /* T = g*g + 1                                    */
     int32_t width;      /* D                                              */
     int32_t layers;     /* L                                              */
-    int32_t heads;      /* D / 64 (head dim must be 64)                   */
+    int32_t heads;      /* D / head_dim                                   */
     int32_t mlp;        /* 4*D                                            */
     int32_t embed;      /* E: output dim of `proj`                        */
     int32_t kpatch;     /* 3*p*p                                          */
     int32_t kpad;       /* kpatch rounded up to a multiple of 64          */
     int32_t act;        /* PCG_ACT_*                                      */
+    int32_t head_dim;   /* 64 (tcgen05 attention), or 80 / 88: ViT-H/14 and  */
+                        /* ViT-g/14, stored padded to 128 columns per head    */
 } pcg_vit_config;
+
+/* Columns one head occupies in qkv / attention-output buffers: head_dim 64 -> 64, wider heads -> 128 (zero padded by
+ * the weight packing).  The attention-side width of a tower is heads * pcg_head_stride(head_dim). */
+int pcg_head_stride(int head_dim);
 
 /* One ResidualAttentionBlock (ruclip/model.py:25-54).  w_* are bf16 [out,in] row-major (nn.Linear layout);
  * w_*_t are their transposes [in,out] used by the dgrad GEMMs.  The 1/sqrt(64) attention scale is folded
- * into the q rows of w_qkv / b_qkv (exact: a power of two). */
+ * into the q rows of w_qkv / b_qkv (exact: a power of two).  With head_dim != 64 every head of q, k, v occupies 128
+ * rows of w_qkv (80 / 88 real + zero rows) and 128 columns of w_out: 3D and D below read 3*Da and Da = heads*128
+ * on the attention side. */
 typedef struct pcg_layer_weights {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
     const void *w_qkv, *w_qkv_t; /* [3D,D], [D,3D] */
@@ -143,6 +151,12 @@ int pcg_attn_fwd(const void *qkv, void *out, float *lse, int n, int T, int heads
 size_t pcg_attn_bwd_workspace_bytes(int n, int T, int heads);
 int pcg_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse, float *delta_ws,
                  void *d_qkv, int n, int T, int heads, void *stream);
+/* Wide heads (head dim 80 / 88 -- ViT-H/14, the default of perceptor/losses/open_clip.py:8-12, and ViT-g/14 --
+ * padded to 128 columns per head): qkv bf16 [n*T, 3*heads*128], out / d_out bf16 [n*T, heads*128], q pre-scaled by
+ * 1/sqrt(head dim), pad columns zero.  Same lse / delta_ws conventions as above. */
+int pcg_attn_fwd_wide(const void *qkv, void *out, float *lse, int n, int T, int heads, void *stream);
+int pcg_attn_bwd_wide(const void *qkv, const void *out, const void *d_out, const float *lse, float *delta_ws,
+                      void *d_qkv, int n, int T, int heads, void *stream);
 
 /* ---- head: ln_post(CLS) @ proj -> L2 normalise -> spherical distance loss, forward AND gradient ---------
  * replaces ruclip/model.py:126-129 + F.normalize (models/open_clip.py:120-121) + CLIP.forward

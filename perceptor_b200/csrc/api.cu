@@ -74,8 +74,8 @@ struct Bump {
 
 struct LayerStash {
     float* xb;     // [M,D]  residual after attention
-    uint16_t* qkv; // [M,3D]
-    uint16_t* o;   // [M,D]
+    uint16_t* qkv; // [M,3Da]  (Da = heads * head stride: D for head dim 64)
+    uint16_t* o;   // [M,Da]
     float* lse;    // [n*heads*T]
     uint16_t* h;   // [M,4D] act'(pre-activation) of the MLP (the derivative is stored, not h)
 };
@@ -92,6 +92,7 @@ struct Stash {
 // when `layers_kept` == 1 every layer aliases the same block (forward-only mode)
 Stash carve_stash(void* base, const pcg_vit_config& c, int n, int layers_kept) {
     const size_t M = static_cast<size_t>(n) * c.tokens, D = c.width;
+    const size_t Da = static_cast<size_t>(c.heads) * pcg_head_stride(c.head_dim);  // attention-side width (padded heads)
     Bump b(base);
     Stash s;
     s.v = b.take<float>(M * D);
@@ -100,8 +101,8 @@ Stash carve_stash(void* base, const pcg_vit_config& c, int n, int layers_kept) {
     s.x0 = b.take<float>(s.x_stride * nx);
     const size_t before = b.off;
     s.layer0.xb = b.take<float>(M * D);
-    s.layer0.qkv = b.take<uint16_t>(M * 3 * D);
-    s.layer0.o = b.take<uint16_t>(M * D);
+    s.layer0.qkv = b.take<uint16_t>(M * 3 * Da);
+    s.layer0.o = b.take<uint16_t>(M * Da);
     s.layer0.lse = b.take<float>(static_cast<size_t>(n) * c.heads * c.tokens);
     s.layer0.h = b.take<uint16_t>(M * c.mlp);
     s.layer_stride = b.off - before;
@@ -139,6 +140,7 @@ struct Work {
 
 Work carve_work(void* base, const pcg_vit_config& c, int n) {
     const size_t M = static_cast<size_t>(n) * c.tokens, D = c.width, P = static_cast<size_t>(n) * c.grid * c.grid;
+    const size_t Da = static_cast<size_t>(c.heads) * pcg_head_stride(c.head_dim);
     Bump b(base);
     Work w;
     w.patches = b.take<uint16_t>(P * c.kpad);
@@ -146,8 +148,8 @@ Work carve_work(void* base, const pcg_vit_config& c, int n) {
     w.y = b.take<uint16_t>(M * D);
     w.a = b.take<uint16_t>(M * c.mlp);
     w.dxb = b.take<uint16_t>(M * D);
-    w.dqkv = b.take<uint16_t>(M * 3 * D);
-    w.d_o = b.take<uint16_t>(M * D);
+    w.dqkv = b.take<uint16_t>(M * 3 * Da);
+    w.d_o = b.take<uint16_t>(M * Da);
     w.delta = b.take<float>(pcg_attn_bwd_workspace_bytes(n, c.tokens, c.heads) / sizeof(float));
     w.head_ws = b.take<float>(pcg_head_workspace_bytes(n, c.width, c.embed) / sizeof(float));
     w.nostash = base ? static_cast<uint8_t*>(base) + b.off : nullptr;
@@ -158,11 +160,13 @@ Work carve_work(void* base, const pcg_vit_config& c, int n) {
 
 int check_cfg(const pcg_vit_config* c) {
     PCG_CHECK_ARG(c != nullptr, "null config");
-    PCG_CHECK_ARG(c->width > 0 && c->width % 128 == 0 && c->heads * 64 == c->width,
-                  "width %d / heads %d: head dim must be 64 and width a multiple of 128", c->width, c->heads);
+    PCG_CHECK_ARG(c->width > 0 && c->width % 128 == 0 && c->heads > 0 && c->heads * c->head_dim == c->width &&
+                      (c->head_dim == 64 || (c->head_dim > 64 && c->head_dim <= 128 && c->head_dim % 8 == 0)),
+                  "width %d / heads %d / head dim %d: need heads * head_dim == width, width a multiple of 128 and a head "
+                  "dim of 64 or 72..128 (padded to 128)", c->width, c->heads, c->head_dim);
     PCG_CHECK_ARG(c->grid * c->patch == c->image_size && c->tokens == c->grid * c->grid + 1, "inconsistent grid/tokens");
     PCG_CHECK_ARG(c->kpatch == 3 * c->patch * c->patch && c->kpad >= c->kpatch && c->kpad % 64 == 0, "bad kpatch/kpad");
-    PCG_CHECK_ARG(c->mlp % 256 == 0 && c->layers > 0 && c->embed > 0, "bad mlp/layers/embed");
+    PCG_CHECK_ARG(c->mlp % 128 == 0 && c->layers > 0 && c->embed > 0, "bad mlp/layers/embed");
     return 0;
 }
 
@@ -197,6 +201,7 @@ using namespace pcg;
 extern "C" const char* pcg_last_error(void) { return last_error_buf(); }
 extern "C" int pcg_abi_version(void) { return PCG_ABI_VERSION; }
 extern "C" int pcg_device_sm_count(void) { return sm_count(); }
+extern "C" int pcg_head_stride(int head_dim) { return head_dim == 64 ? 64 : 128; }
 extern "C" int pcg_last_launch_count(void) { return launch_count(); }
 
 extern "C" int pcg_profile_enable(int on) {
@@ -239,6 +244,8 @@ extern "C" int pcg_guidance_fwd(const pcg_guidance_args* a, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int n = a->n_cut, T = c.tokens, D = c.width;
     const int M = n * T, P = n * c.grid * c.grid;
+    const bool wide = c.head_dim != 64;                      // ViT-H/14, ViT-g/14: heads padded to 128 columns
+    const int Da = c.heads * pcg_head_stride(c.head_dim);    // attention-side width
     const bool keep = a->want_grad != 0;
     Work wk = carve_work(a->workspace, c, n);
     Stash st = keep ? carve_stash(a->stash, c, n, c.layers) : carve_stash(wk.nostash, c, n, 1);
@@ -256,10 +263,11 @@ extern "C" int pcg_guidance_fwd(const pcg_guidance_args* a, void* stream) {
         float* x_in = stash_x(st, l, keep);
         float* x_out = stash_x(st, l + 1, keep);
         PCG_TRY(pcg_layernorm_fwd(x_in, lw.ln1_g, lw.ln1_b, wk.y, M, D, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, 3 * D, D, wk.y, D, lw.w_qkv, D, lw.b_qkv, nullptr, ls.qkv,
-                              nullptr, 3 * D, stream));
-        PCG_TRY(pcg_attn_fwd(ls.qkv, ls.o, ls.lse, n, T, c.heads, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_RESID_F32, c.act, M, D, D, ls.o, D, lw.w_out, D, lw.b_out, x_in, ls.xb, nullptr,
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, 3 * Da, D, wk.y, D, lw.w_qkv, D, lw.b_qkv, nullptr, ls.qkv,
+                              nullptr, 3 * Da, stream));
+        PCG_TRY(wide ? pcg_attn_fwd_wide(ls.qkv, ls.o, ls.lse, n, T, c.heads, stream)
+                     : pcg_attn_fwd(ls.qkv, ls.o, ls.lse, n, T, c.heads, stream));
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_RESID_F32, c.act, M, D, Da, ls.o, Da, lw.w_out, Da, lw.b_out, x_in, ls.xb, nullptr,
                               D, stream));
         PCG_TRY(pcg_layernorm_fwd(ls.xb, lw.ln2_g, lw.ln2_b, wk.y, M, D, stream));
         PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BIAS_ACT, c.act, M, c.mlp, D, wk.y, D, lw.w_fc, D, lw.b_fc, nullptr, ls.h, wk.a,
@@ -280,6 +288,8 @@ extern "C" int pcg_guidance_bwd(const pcg_guidance_args* a, void* stream) {
     const pcg_vit_weights& w = *a->w;
     const int n = a->n_cut, T = c.tokens, D = c.width;
     const int M = n * T, P = n * c.grid * c.grid;
+    const bool wide = c.head_dim != 64;
+    const int Da = c.heads * pcg_head_stride(c.head_dim);
     Work wk = carve_work(a->workspace, c, n);
     Stash st = carve_stash(a->stash, c, n, c.layers);
 
@@ -297,10 +307,11 @@ extern "C" int pcg_guidance_bwd(const pcg_guidance_args* a, void* stream) {
                               nullptr, D, stream));
         PCG_TRY(pcg_layernorm_bwd(wk.y, ls.xb, lw.ln2_g, nullptr, wk.dxb, M, D, stream));
         // attention: dO = dx W_out ; dqkv = attn'(dO) ; dy = dqkv W_qkv ; dx += ln_1'(dy)
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, D, wk.dxb, D, lw.w_out_t, D, nullptr, nullptr, wk.d_o, nullptr,
-                              D, stream));
-        PCG_TRY(pcg_attn_bwd(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, 3 * D, wk.dqkv, 3 * D, lw.w_qkv_t, 3 * D, nullptr, nullptr,
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, Da, D, wk.dxb, D, lw.w_out_t, D, nullptr, nullptr, wk.d_o, nullptr,
+                              Da, stream));
+        PCG_TRY(wide ? pcg_attn_bwd_wide(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream)
+                     : pcg_attn_bwd(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream));
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, 3 * Da, wk.dqkv, 3 * Da, lw.w_qkv_t, 3 * Da, nullptr, nullptr,
                               wk.y, nullptr, D, stream));
         PCG_TRY(pcg_layernorm_bwd(wk.y, stash_x(st, l, true), lw.ln1_g, nullptr, wk.dxb, M, D, stream));
     }

@@ -149,7 +149,7 @@ class CLIP(_TextImageLoss):
 class OpenCLIP(_TextImageLoss):
     _renormalize_targets = False  # perceptor/losses/open_clip.py:58-85 stores encodings as given
 
-    def __init__(self, architecture="ViT-L-14", weights="laion2b_s32b_b82k", *, n_cutouts=None, cut_pow=1.0,
+    def __init__(self, architecture="ViT-H-14", weights="laion2b_s32b_b79k", *, n_cutouts=None, cut_pow=1.0,
                  min_size=None, max_size=None, seed=0, generator=None, process_group=None, shard="cutouts",
                  state_dict=None, weights_seed=0, bpe_path=None):
         """
@@ -157,7 +157,9 @@ class OpenCLIP(_TextImageLoss):
             architecture (str): name of the clip model
             weights (str): name of the weights
 
-        The reference's default (ViT-H-14, head dim 80) is outside the native path's head-dim-64 kernels.
+        Defaults as in the reference (perceptor/losses/open_clip.py:8-12).  ViT-H-14 / ViT-g-14 have head dim 80 / 88:
+        their heads are padded to 128 columns and attention runs on the mma.sync kernels (the tcgen05 attention kernels
+        are head-dim-64: ViT-B/32, B/16, L/14, L/14@336).
         """
         super().__init__()
         self.architecture = architecture

@@ -19,13 +19,15 @@ from . import checkpoints, cutouts, native, text
 from .guidance import EncodeImagesFn, GuidanceEngine
 from .vit import random_state_dict, required_keys, resolve_shape
 
-# (architecture, weights) pairs the reference documents for ViT towers with head dim 64
+# (architecture, weights) pairs the reference documents for ViT towers
 # (perceptor/models/open_clip.py:24-44); anything else raises ValueError like the reference does (:52-53).
 _PRETRAINED = {
     ("ViT-B-32-quickgelu", "openai"), ("ViT-B-32", "openai"), ("ViT-B-16", "openai"), ("ViT-L-14", "openai"),
     ("ViT-L-14-336", "openai"),
     ("ViT-B-32", "laion2b_s34b_b79k"), ("ViT-B-32", "laion2b_e16"), ("ViT-B-32", "laion400m_e32"),
     ("ViT-B-16", "laion400m_e32"), ("ViT-L-14", "laion2b_s32b_b82k"), ("ViT-L-14", "laion400m_e32"),
+    # head dim 80 / 88: heads padded to 128 columns, attention on the mma.sync kernels (perceptor/models/open_clip.py:24-27)
+    ("ViT-H-14", "laion2b_s32b_b79k"), ("ViT-g-14", "laion2b_s12b_b42k"),
 }
 
 

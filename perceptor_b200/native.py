@@ -16,7 +16,7 @@ LIB_PATH = PKG_DIR / "libpcg.so"
 ACT_QUICKGELU, ACT_GELU = 0, 1
 GEMM_BF16, GEMM_BIAS_ACT, GEMM_RESID_F32, GEMM_DACT, GEMM_F32 = 0, 1, 2, 3, 4
 CUT_STRIDE = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -26,7 +26,8 @@ class VitConfig(C.Structure):
     """pcg_vit_config"""
 
     _fields_ = [(n, C.c_int32) for n in (
-        "image_size", "patch", "grid", "tokens", "width", "layers", "heads", "mlp", "embed", "kpatch", "kpad", "act")]
+        "image_size", "patch", "grid", "tokens", "width", "layers", "heads", "mlp", "embed", "kpatch", "kpad", "act",
+        "head_dim")]
 
 
 class LayerWeights(C.Structure):
@@ -86,9 +87,12 @@ SIGNATURES = {
     "pcg_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "pcg_embed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pcg_head_stride": (_i, [_i]),
     "pcg_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_attn_bwd_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "pcg_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pcg_attn_fwd_wide": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pcg_attn_bwd_wide": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_head_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcg_head_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "pcg_workspace_bytes": (C.c_size_t, [C.POINTER(VitConfig), _i]),

@@ -85,6 +85,24 @@ def attn_bwd(qkv, out, d_out, lse, n, tokens, heads):
     return d_qkv
 
 
+def attn_fwd_wide(qkv, n, tokens, heads):
+    """Heads wider than 64 (80 / 88), stored padded to 128 columns: qkv [n*T, 3*heads*128]."""
+    out = torch.empty((n * tokens, heads * 128), dtype=bf16, device=qkv.device)
+    lse = torch.empty((n, heads, tokens), dtype=torch.float32, device=qkv.device)
+    native.check(native.lib().pcg_attn_fwd_wide(_p(qkv), _p(out), _p(lse), n, tokens, heads, native.stream_ptr()),
+                 "pcg_attn_fwd_wide")
+    return out, lse
+
+
+def attn_bwd_wide(qkv, out, d_out, lse, n, tokens, heads):
+    d_qkv = torch.empty_like(qkv)
+    delta = torch.empty(native.lib().pcg_attn_bwd_workspace_bytes(n, tokens, heads) // 4, dtype=torch.float32,
+                        device=qkv.device)
+    native.check(native.lib().pcg_attn_bwd_wide(_p(qkv), _p(out), _p(d_out), _p(lse), _p(delta), _p(d_qkv), n, tokens,
+                                                heads, native.stream_ptr()), "pcg_attn_bwd_wide")
+    return d_qkv
+
+
 def head_loss(x, ln_g, ln_b, proj, targets, tweights, n, tokens, scale=1.0, normalize=True, want_grad=True,
               d_enc=None):
     d, e = proj.shape

@@ -157,6 +157,7 @@ class TextShape:
 TEXT_SHAPES = {
     "ViT-B-32": TextShape(512, 8, 12, 512), "ViT-B-16": TextShape(512, 8, 12, 512),
     "ViT-L-14": TextShape(768, 12, 12, 768), "ViT-L-14-336": TextShape(768, 12, 12, 768),
+    "ViT-H-14": TextShape(1024, 16, 24, 1024), "ViT-g-14": TextShape(1024, 16, 24, 1024),  # open_clip model_configs
 }
 
 

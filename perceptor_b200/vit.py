@@ -28,6 +28,17 @@ class VitShape:
     layers: int
     heads: int
     embed: int
+    mlp_width: int = 0  # 0: 4 * width (every OpenAI tower); open_clip's ViT-g-14 uses 6144 = 4.36 x 1408
+
+    @property
+    def head_dim(self) -> int:
+        return self.width // self.heads
+
+    @property
+    def head_stride(self) -> int:
+        """Columns one head occupies in the qkv / attention-output buffers (include/pcg.h: pcg_head_stride): heads wider
+        than 64 (ViT-H/14: 80, ViT-g/14: 88) are zero padded to 128."""
+        return 64 if self.head_dim == 64 else 128
 
     @property
     def grid(self) -> int:
@@ -39,7 +50,7 @@ class VitShape:
 
     @property
     def mlp(self) -> int:
-        return 4 * self.width
+        return self.mlp_width or 4 * self.width
 
     @property
     def kpatch(self) -> int:
@@ -53,7 +64,7 @@ class VitShape:
         """Algorithmic forward+backward FLOPs per cutout (dgrad-only backward; SURVEY.md §8d / BASELINE.md §4)."""
         g2, d, t, l = self.grid**2, self.width, self.tokens, self.layers
         patch = 2 * g2 * self.kpatch * d
-        linear = l * t * 24 * d * d
+        linear = l * t * (8 * d * d + 4 * d * self.mlp)  # QKV 6D^2 + out 2D^2 + MLP 2 * 2 * D * mlp per token
         attn = l * 4 * t * t * d
         head = 2 * d * self.embed
         return (patch + linear + attn + head) + (patch + linear + 2 * attn + head)
@@ -64,6 +75,10 @@ SHAPES = {
     "ViT-B-16": VitShape(224, 16, 768, 12, 12, 512),
     "ViT-L-14": VitShape(224, 14, 1024, 24, 16, 768),
     "ViT-L-14-336": VitShape(336, 14, 1024, 24, 16, 768),
+    # open_clip model_configs/ViT-H-14.json / ViT-g-14.json (head dim 80 / 88: perceptor/models/open_clip.py:24-27,
+    # the reference's OpenCLIP default is ViT-H-14, perceptor/losses/open_clip.py:8-12)
+    "ViT-H-14": VitShape(224, 14, 1280, 32, 16, 1024),
+    "ViT-g-14": VitShape(224, 14, 1408, 40, 16, 1024, mlp_width=6144),
 }
 
 
@@ -72,7 +87,7 @@ def resolve_shape(architecture: str) -> tuple[str, VitShape]:
     name = architecture.replace("-quickgelu", "").replace("-336px", "-336")
     if name not in SHAPES:
         raise ValueError(
-            f"Invalid architecture: {architecture} (the native path covers {sorted(SHAPES)}; head dim must be 64)")
+            f"Invalid architecture: {architecture} (the native path covers {sorted(SHAPES)})")
     return name, SHAPES[name]
 
 
@@ -105,10 +120,11 @@ def random_state_dict(shape: VitShape, seed: int = 0, dtype=torch.float32) -> di
         sd[p + "attn.in_proj_bias"] = torch.zeros(3 * d, dtype=dtype)
         sd[p + "attn.out_proj.weight"] = uniform((d, d), 1 / math.sqrt(d))
         sd[p + "attn.out_proj.bias"] = torch.zeros(d, dtype=dtype)
-        sd[p + "mlp.c_fc.weight"] = uniform((4 * d, d), 1 / math.sqrt(d))
-        sd[p + "mlp.c_fc.bias"] = uniform((4 * d,), 1 / math.sqrt(d))
-        sd[p + "mlp.c_proj.weight"] = uniform((d, 4 * d), 1 / math.sqrt(4 * d))
-        sd[p + "mlp.c_proj.bias"] = uniform((d,), 1 / math.sqrt(4 * d))
+        m = shape.mlp
+        sd[p + "mlp.c_fc.weight"] = uniform((m, d), 1 / math.sqrt(d))
+        sd[p + "mlp.c_fc.bias"] = uniform((m,), 1 / math.sqrt(d))
+        sd[p + "mlp.c_proj.weight"] = uniform((d, m), 1 / math.sqrt(m))
+        sd[p + "mlp.c_proj.bias"] = uniform((d,), 1 / math.sqrt(m))
     return sd
 
 
@@ -164,11 +180,23 @@ class PackedWeights:
             p = f"transformer.resblocks.{i}."
             w_in = sd[p + "attn.in_proj_weight"].detach().to(dev, torch.float32).clone()
             b_in = sd[p + "attn.in_proj_bias"].detach().to(dev, torch.float32).clone()
-            # fold the 1/sqrt(head_dim) = 1/8 attention scale into the q projection (exact in bf16)
-            w_in[:d] *= 0.125
-            b_in[:d] *= 0.125
+            # fold the 1/sqrt(head_dim) attention scale into the q projection (1/8 for head dim 64: exact in bf16)
+            w_in[:d] *= shape.head_dim ** -0.5
+            b_in[:d] *= shape.head_dim ** -0.5
+            w_o = sd[p + "attn.out_proj.weight"].detach().to(dev, torch.float32)
+            if shape.head_stride != shape.head_dim:
+                # wide heads: head h of q / k / v moves to rows [h*128, h*128 + head_dim) of its third, the rest are zero
+                # rows (so the pad columns of qkv are exactly zero); out_proj gets matching zero columns
+                hd, hs, nh = shape.head_dim, shape.head_stride, shape.heads
+                w_pad = torch.zeros(3, nh, hs, d, device=dev)
+                w_pad[:, :, :hd] = w_in.reshape(3, nh, hd, d)
+                b_pad = torch.zeros(3, nh, hs, device=dev)
+                b_pad[:, :, :hd] = b_in.reshape(3, nh, hd)
+                o_pad = torch.zeros(d, nh, hs, device=dev)
+                o_pad[:, :, :hd] = w_o.reshape(d, nh, hd)
+                w_in, b_in, w_o = w_pad.reshape(3 * nh * hs, d), b_pad.reshape(3 * nh * hs), o_pad.reshape(d, nh * hs)
             w_qkv, w_qkv_t = both(w_in)
-            w_out, w_out_t = both(sd[p + "attn.out_proj.weight"])
+            w_out, w_out_t = both(w_o)
             w_fc, w_fc_t = both(sd[p + "mlp.c_fc.weight"])
             w_proj, w_proj_t = both(sd[p + "mlp.c_proj.weight"])
             lw = self.layers_c[i]
@@ -185,7 +213,7 @@ class PackedWeights:
         self.cfg = native.VitConfig(
             image_size=shape.image_size, patch=shape.patch, grid=shape.grid, tokens=shape.tokens, width=shape.width,
             layers=shape.layers, heads=shape.heads, mlp=shape.mlp, embed=shape.embed, kpatch=shape.kpatch,
-            kpad=shape.kpad, act=act)
+            kpad=shape.kpad, act=act, head_dim=shape.head_dim)
         self.weights_c = native.VitWeights(
             conv1=self.conv1.data_ptr(), conv1_t=self.conv1_t.data_ptr(), cls=self.cls.data_ptr(),
             pos=self.pos.data_ptr(), ln_pre_g=self.ln_pre_g.data_ptr(), ln_pre_b=self.ln_pre_b.data_ptr(),

@@ -38,7 +38,8 @@ def test_sizing_queries_need_no_gpu():
 
     s = SHAPES["ViT-L-14"]
     cfg = native.VitConfig(image_size=s.image_size, patch=s.patch, grid=s.grid, tokens=s.tokens, width=s.width,
-                           layers=s.layers, heads=s.heads, mlp=s.mlp, embed=s.embed, kpatch=s.kpatch, kpad=s.kpad, act=0)
+                           layers=s.layers, heads=s.heads, mlp=s.mlp, embed=s.embed, kpatch=s.kpatch, kpad=s.kpad, act=0,
+                           head_dim=s.head_dim)
     lib = native.lib()
     ws, st = lib.pcg_workspace_bytes(ctypes.byref(cfg), 128), lib.pcg_stash_bytes(ctypes.byref(cfg), 128)
     m = 128 * 257
@@ -46,6 +47,15 @@ def test_sizing_queries_need_no_gpu():
     assert st >= 24 * per_layer and st < 1.2 * (24 * per_layer + 26 * m * 1024 * 4)
     assert ws > 0 and lib.pcg_workspace_bytes(ctypes.byref(cfg), 0) == 0
     assert lib.pcg_stash_bytes(ctypes.byref(cfg), 256) > st
+    # wide heads (ViT-H/14: head dim 80) are stored padded to 128 columns: the attention-side buffers grow accordingly
+    assert lib.pcg_head_stride(64) == 64 and lib.pcg_head_stride(80) == 128 and lib.pcg_head_stride(88) == 128
+    h = SHAPES["ViT-H-14"]
+    cfg_h = native.VitConfig(image_size=h.image_size, patch=h.patch, grid=h.grid, tokens=h.tokens, width=h.width,
+                             layers=h.layers, heads=h.heads, mlp=h.mlp, embed=h.embed, kpatch=h.kpatch, kpad=h.kpad, act=1,
+                             head_dim=h.head_dim)
+    mh = 4 * 257
+    per_layer_h = mh * 1280 * 4 + mh * 3 * 2048 * 2 + mh * 2048 * 2 + mh * 5120 * 2
+    assert lib.pcg_stash_bytes(ctypes.byref(cfg_h), 4) >= 32 * per_layer_h
 
 
 def test_argument_errors_return_negative_codes_and_messages():

@@ -682,3 +682,54 @@ def test_aesthetic_visual_assessment_head_matches_oracle(cuda_device):
         ref.backward()
         assert abs(float(v) - float(ref)) <= LOSS_RTOL * abs(float(ref)) + 1e-6, (mode, float(v), float(ref))
         assert cosine(x.grad.cpu(), ref_img.grad) >= GRAD_COS, (mode, cosine(x.grad.cpu(), ref_img.grad))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# wide heads: ViT-H/14 (head dim 80, the reference's OpenCLIP default) and ViT-g/14 (88)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("width,heads,mlp", [(640, 8, 0), (1408, 16, 2816)])  # head dim 80 / 88
+def test_wide_head_towers_match_oracle(cuda_device, width, heads, mlp):
+    """A short tower with ViT-H/14's (80) resp. ViT-g/14's (88) head dim through the whole path: padded qkv layout,
+    mma.sync attention over two 64-column blocks, out-proj with K = heads * 128; exact-GELU like the LAION weights."""
+    shape = VitShape(image_size=56, patch=14, width=width, layers=2, heads=heads, embed=32, mlp_width=mlp)
+    assert shape.head_dim in (80, 88) and shape.head_stride == 128
+    sd = perturb(random_state_dict(shape, 13))
+    g = torch.Generator().manual_seed(13)
+    images = torch.rand(1, 3, 96, 80, generator=g)
+    rows = [(0, 0, 0, 80), (0, 20, 10, 56), (0, 30, 0, 64)]
+    targets = torch.nn.functional.normalize(torch.randn(2, shape.embed, generator=g))
+    tw = torch.tensor([1.0, -0.4])
+    img_ref = images.clone().requires_grad_()
+    loss_ref = guidance_oracle.guidance_loss(img_ref, rows, sd, shape.image_size, shape.patch, shape.layers, shape.heads,
+                                             targets, tw, 1.0, act="gelu")
+    loss_ref.backward()
+    eng = GuidanceEngine(shape, sd, cuda_device, native.ACT_GELU)
+    img = images.to(cuda_device).requires_grad_()
+    loss = GuidanceLossFn.apply(img, eng, eng.plan_cutouts(np.asarray(rows, dtype=np.int32)), targets.to(cuda_device),
+                                tw.to(cuda_device), 1.0, None)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_RTOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    assert cosine(img.grad.cpu(), img_ref.grad) >= GRAD_COS, cosine(img.grad.cpu(), img_ref.grad)
+
+
+def test_open_clip_default_is_vit_h_14_like_the_reference(cuda_device):
+    """losses.OpenCLIP() with NO arguments = ViT-H-14 / laion2b_s32b_b79k (perceptor/losses/open_clip.py:8-12): 632 M
+    parameters, 32 layers, 16 heads x 80, exact GELU.  Two cutouts against the fp32 oracle."""
+    loss_mod = losses.OpenCLIP(n_cutouts=2, min_size=160, seed=4)
+    assert loss_mod.architecture == "ViT-H-14" and loss_mod.model.shape.head_dim == 80 and loss_mod.model.act == native.ACT_GELU
+    shape = loss_mod.model.shape
+    g = torch.Generator().manual_seed(41)
+    targets = torch.nn.functional.normalize(torch.randn(2, shape.embed, generator=g))
+    loss_mod.add_encodings_(targets, [1.0, 0.5])
+    images = torch.rand(1, 3, 256, 256, generator=g)
+    img = images.to(cuda_device).requires_grad_()
+    loss = loss_mod(img)
+    loss.backward()
+    rows = loss_mod.last_cutouts.tolist()
+    sd = {k: v.detach().float().cpu() for k, v in loss_mod.model.state_dict_openai().items()}
+    img_ref = images.clone().requires_grad_()
+    loss_ref = guidance_oracle.guidance_loss(img_ref, rows, sd, shape.image_size, shape.patch, shape.layers, shape.heads,
+                                             targets, torch.tensor([1.0, 0.5]), 1.0, act="gelu")
+    loss_ref.backward()
+    assert abs(float(loss) - float(loss_ref)) <= LOSS_RTOL * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    assert cosine(img.grad.cpu(), img_ref.grad) >= GRAD_COS, cosine(img.grad.cpu(), img_ref.grad)

@@ -216,6 +216,39 @@ def run_attention_case(cuda_device, n, t, heads, tc):
         check_close(d_qkv[:, sl], ref.grad[:, sl], 1.5e-2, f"attention {name} T={t} tc={tc}")
 
 
+@pytest.mark.parametrize("n,t,heads,hd", [(2, 257, 16, 80), (1, 257, 4, 88), (3, 50, 2, 80), (1, 197, 3, 88), (2, 64, 1, 80),
+                                          (1, 130, 2, 128), (1, 577, 2, 80)])
+def test_attention_wide_heads(cuda_device, n, t, heads, hd):
+    """Head dim 80 (ViT-H/14), 88 (ViT-g/14), stored padded to 128 columns per head: the mma.sync kernels over two
+    64-column blocks, against fp32 torch on the UNPADDED problem; the pad columns must stay exactly zero."""
+    g = torch.Generator(device="cpu").manual_seed(t + heads + hd)
+    q, k, v = (torch.randn(n, t, heads, hd, generator=g) for _ in range(3))
+    q = q * hd**-0.5 * 2.0  # pre-scaled queries, logits O(1)
+    d_o = torch.randn(n, t, heads, hd, generator=g)
+
+    def padded(x):  # [n, t, heads, hd] -> [n*t, heads*128] bf16
+        out = torch.zeros(n, t, heads, 128)
+        out[..., :hd] = x
+        return out.reshape(n * t, heads * 128)
+
+    qkv = torch.cat([padded(q), padded(k), padded(v)], dim=1).to(cuda_device, bf16)
+    out, lse = ops.attn_fwd_wide(qkv, n, t, heads)
+    qr, kr, vr = (x.to(cuda_device, bf16).float().requires_grad_() for x in (q, k, v))
+    s = torch.einsum("nqhd,nkhd->nhqk", qr, kr)
+    o_ref = torch.einsum("nhqk,nkhd->nqhd", torch.softmax(s, dim=-1), vr)
+    out4 = out.float().reshape(n, t, heads, 128)
+    assert float(out4[..., hd:].abs().max()) == 0.0 if hd < 128 else True
+    check_close(out4[..., :hd], o_ref, 6e-3, f"wide attention fwd hd={hd}")
+    check_close(lse, torch.logsumexp(s, dim=-1), 1e-3, f"wide attention lse hd={hd}")
+    d_out = padded(d_o).to(cuda_device, bf16)
+    o_ref.backward(d_o.to(cuda_device, bf16).float())
+    d_qkv = ops.attn_bwd_wide(qkv, out, d_out, lse, n, t, heads).float().reshape(n, t, 3, heads, 128)
+    if hd < 128:
+        assert float(d_qkv[..., hd:].abs().max()) == 0.0
+    for i, (name, ref) in enumerate((("dq", qr.grad), ("dk", kr.grad), ("dv", vr.grad))):
+        check_close(d_qkv[:, :, i, :, :hd], ref, 1.5e-2, f"wide attention {name} hd={hd}")
+
+
 def test_attention_random_shapes_repeated(cuda_device):
     """Every tensor-core path (packed T <= 64, fused 66..257, streaming > 257) on seeded random shapes, each run twice
     on fresh data: a race between the elementwise warps and the MMA pipe (P^T / dS^T buffers reused across blocks)

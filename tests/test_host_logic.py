@@ -114,7 +114,12 @@ def test_shapes_and_flop_model_match_baseline_table():
     assert SHAPES["ViT-L-14"].tokens == 257 and SHAPES["ViT-L-14"].kpad == 640 and SHAPES["ViT-B-32"].kpad == 3072
     assert resolve_shape("ViT-B-32-quickgelu")[0] == "ViT-B-32" and resolve_shape("ViT-L-14-336px")[0] == "ViT-L-14-336"
     with pytest.raises(ValueError):
-        resolve_shape("ViT-H-14")
+        resolve_shape("ViT-bigG-14")
+    # wide heads (the reference's OpenCLIP default is ViT-H-14): head dim 80 / 88, stored padded to 128 columns
+    h, g14 = SHAPES["ViT-H-14"], SHAPES["ViT-g-14"]
+    assert (h.head_dim, h.head_stride, h.mlp, h.tokens) == (80, 128, 5120, 257)
+    assert (g14.head_dim, g14.head_stride, g14.mlp) == (88, 128, 6144) and SHAPES["ViT-L-14"].head_stride == 64
+    assert abs(h.flops_per_cutout() / 1e9 - 680.0) <= 3.0  # "ViT-H/14: 680 GF"
     sd = random_state_dict(SHAPES["ViT-B-32"], 0)
     assert set(required_keys(12)) == set(sd)
     assert sd["conv1.weight"].shape == (768, 3, 32, 32) and sd["proj"].shape == (768, 512)
@@ -142,8 +147,12 @@ def test_module_surface_and_error_behaviour_without_gpu(tmp_path):
     # no CPU fallback: the image path must fail loudly off-GPU
     with pytest.raises(RuntimeError):
         loss(torch.rand(1, 3, 64, 64))
-    with pytest.raises(FileNotFoundError, match="merge table"):  # the BPE vocabulary is user-supplied data
-        loss.add_texts_(["hello"])
+    # add_texts_ works out of the box with the packaged CLIP merge table (text tower in plain torch, CPU is fine)
+    before = loss.encodings.shape[0]
+    loss.add_texts_(["hello world"], [0.5])
+    assert loss.encodings.shape == (before + 1, 512) and abs(float(loss.encodings[-1].norm()) - 1.0) < 1e-5
+    with pytest.raises(FileNotFoundError, match="merge table"):
+        losses.CLIP("ViT-B-32", bpe_path=str(tmp_path / "missing.gz")).add_texts_(["hello"])
     stub = tmp_path / "textoff.json"
     stub.write_text('{"ViT-B-32": [[0.1, 0.2]]}')
     with pytest.raises(ValueError, match="There is no textoff"):  # perceptor/losses/clip/clip.py:57-58
