@@ -214,11 +214,13 @@ __global__ void __launch_bounds__(kRowThreads) embed_bwd_kernel(const void* __re
         case 1: KERNEL<1><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
         case 2: KERNEL<2><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
         case 4: KERNEL<4><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
+        case 5: KERNEL<5><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
         case 6: KERNEL<6><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
         case 8: KERNEL<8><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                             \
         case 10: KERNEL<10><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                           \
+        case 11: KERNEL<11><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                           \
         case 12: KERNEL<12><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                           \
-        default: return ::pcg::set_error(-1, "width %d is not one of 128*{1,2,4,6,8,10,12}", (D));           \
+        default: return ::pcg::set_error(-1, "width %d is not one of 128*{1,2,4,5,6,8,10,11,12}", (D));           \
     }
 
 // the same for kernels templated on <NV, bool>
@@ -227,11 +229,13 @@ __global__ void __launch_bounds__(kRowThreads) embed_bwd_kernel(const void* __re
         case 1: KERNEL<1, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
         case 2: KERNEL<2, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
         case 4: KERNEL<4, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
+        case 5: KERNEL<5, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
         case 6: KERNEL<6, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
         case 8: KERNEL<8, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                       \
         case 10: KERNEL<10, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                     \
+        case 11: KERNEL<11, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                     \
         case 12: KERNEL<12, FLAG><<<GRID, kRowThreads, 0, STREAM>>>(__VA_ARGS__); break;                     \
-        default: return ::pcg::set_error(-1, "width %d is not one of 128*{1,2,4,6,8,10,12}", (D));           \
+        default: return ::pcg::set_error(-1, "width %d is not one of 128*{1,2,4,5,6,8,10,11,12}", (D));           \
     }
 
 // --------------------------------------------------------------------------------------------------------
