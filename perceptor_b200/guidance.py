@@ -97,13 +97,14 @@ class GuidanceEngine:
     def _method_for_size(self, s: int) -> int:
         return LANCZOS3 if s >= self.shape.image_size else CUBIC
 
-    def plan_cutouts(self, rows: np.ndarray, rank: int = 0, world: int = 1, b_offset: int = 0) -> CutPlan:
+    def plan_cutouts(self, rows: np.ndarray, rank: int = 0, world: int = 1, b_offset: int | None = None) -> CutPlan:
         """rows: [N,4] square cutouts (b,y0,x0,size) or [N,5] boxes (b,y0,x0,h,w) of ALL ranks; this rank takes the
-        contiguous shard `cutouts.shard_rows(N, rank, world)`.  `b_offset` re-bases the image index of the shard when
-        the rank holds only its own images (image-sharded mode: global image b is local image b - b_offset)."""
+        contiguous shard `cutouts.shard_rows(N, rank, world)`.  `b_offset` (not None: image-sharded mode) re-bases the
+        image index of the shard: the rank holds only its own images, global image b is local image b - b_offset, and
+        `plan.rows` are the local, re-based rows (what the engine validates against the images it is given)."""
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         n_total = rows.shape[0]
-        local = cutouts.local_rows(rows, rank, world, b_offset)
+        local = cutouts.local_rows(rows, rank, world, b_offset or 0)
         r = self.shape.image_size
         dev = np.zeros((local.shape[0], native.CUT_STRIDE), dtype=np.int32)
         if local.shape[0]:
@@ -127,7 +128,7 @@ class GuidanceEngine:
         table = torch.from_numpy(dev).pin_memory().to(self.device, non_blocking=True) if local.shape[0] else \
             torch.zeros((0, native.CUT_STRIDE), dtype=torch.int32, device=self.device)
         max_in_w = int(dev[:, 4].max()) if local.shape[0] else 1
-        return CutPlan(rows if not b_offset else local, table, n_total, local.shape[0], max_in_w, tabs_c, tab_tensors)
+        return CutPlan(rows if b_offset is None else local, table, n_total, local.shape[0], max_in_w, tabs_c, tab_tensors)
 
     def prebuild_tables(self, min_size: int, max_size: int) -> None:
         self.tables.ensure_sizes(range(min_size, max_size + 1), self._method_for_size)
