@@ -831,8 +831,8 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
             const float inv = 1.0f / sum;
             // the tensor pipe needs ~1000 clk for O: take the next item's edge score now if its Q tile and edge vectors
             // have already landed (they usually have; both barriers stay complete until this warp's item it + 1)
-            if (it + 1 < n_my && mbar_try_wait(&bars[kB2XReady + (s ^ 1)], ((it + 1) >> 1) & 1) &&
-                mbar_try_wait(&bars[kB2FullQK + (s ^ 1)], ((it + 1) >> 1) & 1)) {
+            if (it + 1 < n_my && mbar_test_wait(&bars[kB2XReady + (s ^ 1)], ((it + 1) >> 1) & 1) &&
+                mbar_test_wait(&bars[kB2FullQK + (s ^ 1)], ((it + 1) >> 1) & 1)) {
                 sx_next = row_dot(sm_q0 + (s ^ 1) * kBlkBytes, r, xvec + 192 * (s ^ 1));
                 have_sx = true;
             }
@@ -1586,6 +1586,575 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+// Two independent 32-column accumulator slices at once (the persistent backward's drains): both tensor-memory loads
+// are issued before either is consumed, and the rows go straight to global memory from the tensor-memory layout
+// (thread = row): a drain is one warp's dependent chain, and the staging round trip that makes the one-shot kernel's
+// stores row-coalesced (store -> sync -> load -> store, ~600 clk) costs more here than the extra store transactions.
+// Out of line: the three drains share one copy of the code.
+__device__ __noinline__ void bwd_epilogue2(uint32_t taddr_a, float coef_a, const float* xrow_a, bf16* gbase_a, int row0_a,
+                                           uint32_t taddr_b, float coef_b, const float* xrow_b, bf16* gbase_b, int row0_b,
+                                           int lane, size_t ld, int row_end) {
+    uint32_t va[32], vb[32];
+    tmem_ld<32>(taddr_a, va);
+    tmem_ld<32>(taddr_b, vb);
+    tmem_wait_ld();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t(&v)[32] = half == 0 ? va : vb;
+        const float coef = half == 0 ? coef_a : coef_b;
+        const float* xrow = half == 0 ? xrow_a : xrow_b;
+        const int row = (half == 0 ? row0_a : row0_b) + lane;
+        bf16* grow = (half == 0 ? gbase_a : gbase_b) + static_cast<size_t>(row) * ld;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 xa = *reinterpret_cast<const float4*>(xrow + g * 8);
+            const float4 xb = *reinterpret_cast<const float4*>(xrow + g * 8 + 4);
+            const uint4 o = make_uint4(pack_bf16(fmaf(coef, xa.x, __uint_as_float(v[8 * g])),
+                                                 fmaf(coef, xa.y, __uint_as_float(v[8 * g + 1]))),
+                                       pack_bf16(fmaf(coef, xa.z, __uint_as_float(v[8 * g + 2])),
+                                                 fmaf(coef, xa.w, __uint_as_float(v[8 * g + 3]))),
+                                       pack_bf16(fmaf(coef, xb.x, __uint_as_float(v[8 * g + 4])),
+                                                 fmaf(coef, xb.y, __uint_as_float(v[8 * g + 5]))),
+                                       pack_bf16(fmaf(coef, xb.z, __uint_as_float(v[8 * g + 6])),
+                                                 fmaf(coef, xb.w, __uint_as_float(v[8 * g + 7]))));
+            // thread = row: four 16-byte stores cover this row's 64 contiguous bytes (two full 32-byte sectors)
+            if (row < row_end) *reinterpret_cast<uint4*>(grow + g * 8) = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward, persistent (the production kernel for 130 <= T <= 257: two key tiles, two query blocks)
+// ---------------------------------------------------------------------------------------------------------
+// Same arithmetic, tensor-memory plan and block order as attn_bwd_tc_kernel, but one CTA per SM walks the (cutout,
+// head) items w = blockIdx.x + it * gridDim.x, and three things that kernel does in sequence run beside the block
+// pipeline here (measured on its phase trace: ~5000 clk of operand loads + delta before the first block, ~2800 clk of
+// dV_0 / dK_0 epilogue between the key tiles, ~4200 clk of epilogues at the end, of a 28 300 clk CTA):
+//   * the operand tiles of item it + 1 are requested as soon as the last MMA that reads their slot has retired
+//     (V_0 during block 1, K_0 during block 2, Q_0 / dO_0 during block 3, the second halves at the item's end), so the
+//     first scores of the next item are issued right behind the last block's gradient products;
+//   * four auxiliary warps (one per tensor-memory lane quarter) own everything that is not the 128 x 128 block
+//     arithmetic: the edge token's row and column, lse / delta / edge vectors of the NEXT item (double buffered), and
+//     all six accumulator epilogues -- the eight elementwise warps go from block to block without ever draining;
+//   * barriers complete once per block (S ready, P / dS halves stored), per key tile (dV_j, dK_j complete / drained)
+//     or per item, and every wait names the completion it needs by its running index.
+// Warps: 0-7 elementwise (lane quarter = warp & 3, column phase = warp >> 2), 8 TMA + MMA issue, 9-12 auxiliary
+// (lane quarter = warp & 3 = 1, 2, 3, 0).
+constexpr int kPbEdge = 3;   // edge warps 9..11: the edge token's row and column, next item's lse / edge vectors
+constexpr int kPbDrain = 4;  // drain warps 12..15 (lane quarters 0..3): accumulator epilogues, next item's delta
+constexpr int kPbAux = kPbEdge + kPbDrain;  // 16 warps = 4 per scheduler: 128 registers (a 17th caps the kernel at 96)
+constexpr int kPbThreads = (9 + kPbAux) * 32;
+constexpr int kPbOffStage = 12 * kBlkBytes;               // 4 drain warps x [32 rows x 64 B] (+ 3 unused slices)
+constexpr int kPbOffVec = kPbOffStage + kPbAux * 2048;         // 2 slots x float[256] x 6: lse2, delta, pcol, dscol, prow, dsrow
+constexpr int kPbOffX = kPbOffVec + 2 * 6 * 1024;         // 2 slots x {float[64] x 4: q_x, k_x, v_x, dO_x; 8 scalars}
+constexpr int kPbXFloats = 4 * 64 + 8;
+constexpr int kPbOffBar = kPbOffX + 2 * kPbXFloats * 4;
+constexpr int kPbSmemBytes = kPbOffBar + 20 * 8 + 64 + 1024;  // <= 20 mbarriers + tmem slot
+enum {
+    kPbFullK0 = 0, kPbFullV0 = 1, kPbFullQD0 = 2, kPbFull1 = 3,  // operand tiles landed (TMA)
+    kPbSReady = 4,      // S^T / dP^T of a block retired                       (per block)
+    kPbHalf1 = 5,       // first half of every warp's P^T / dS^T columns stored (per block, 8 warps)
+    kPbHalf2 = 6,       // second half                                          (per block, 8 warps)
+    kPbTileDone = 7,    // dV_j / dK_j complete                                 (per key tile)
+    kPbDqDone = 8,      // every MMA of the item retired                        (per item)
+    kPbAccFreeVK = 9,   // dV / dK drained by the 4 aux warps                   (per key tile)
+    kPbAccFreeQ = 10,   // dQ_0 / dQ_1 drained                                  (per item)
+    kPbEdgeDone = 11,   // aux warps are done reading the operand tiles         (per item)
+    kPbVecReady = 12,   // [2] lse2 / delta / edge vectors of the slot's item   (per use of the slot)
+    kPbGateK0 = 14,     // last reader of K_0 retired                           (per item)
+    kPbGateQD0 = 15,    // last reader of Q_0 / dO_0 retired                    (per item)
+    kPbSlotFree = 16,   // [2] drain warps are done with the slot's vectors     (per use of the slot)
+    kPbRowA = 18,       // edge row of key tile 0 (prow / dsrow, t < 128) ready  (per item, 3 edge warps)
+    kPbCount = 19
+};
+
+struct PbParams {
+    int T, heads;
+    int nv;     // T - 1 in (128, 256]
+    int items;  // n * heads
+    const bf16* qkv;
+    const bf16* out;
+    const bf16* d_out;
+    const float* lse;
+    bf16* d_qkv;
+    long long* trace;
+};
+
+__global__ void __launch_bounds__(kPbThreads, 1)
+attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                        const PbParams p) {
+    grid_dep_launch();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sm_q = sm + kBwdOffQ;
+    uint8_t* sm_k = sm + kBwdOffK;
+    uint8_t* sm_v = sm + kBwdOffV;
+    uint8_t* sm_do = sm + kBwdOffDO;
+    uint8_t* sm_dst = sm + kBwdOffDST;
+    float* vec0 = reinterpret_cast<float*>(sm + kPbOffVec);  // slot s: + 1536 s; lse2, delta, pcol, dscol, prow, dsrow
+    float* x0 = reinterpret_cast<float*>(sm + kPbOffX);       // slot s: + kPbXFloats s; q_x, k_x, v_x, dO_x, scalars
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kPbOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPbCount);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = p.heads * kHd, nv = p.nv;
+    const int G = gridDim.x;
+    const int n_my = (p.items - static_cast<int>(blockIdx.x) + G - 1) / G;
+    const size_t cta_id = blockIdx.x;
+    const int w1 = min(128, ((nv - 128) + 15) & ~15);  // width of query block 1 (block 0 is full)
+    auto decode = [&](int it, int& n, int& h) {
+        const int w = static_cast<int>(blockIdx.x) + it * G;
+        n = w / p.heads;
+        h = w - n * p.heads;
+    };
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(&bars[kPbFullK0], 1);
+            mbar_init(&bars[kPbFullV0], 1);
+            mbar_init(&bars[kPbFullQD0], 1);
+            mbar_init(&bars[kPbFull1], 1);
+            mbar_init(&bars[kPbSReady], 1);
+            mbar_init(&bars[kPbHalf1], 8);
+            mbar_init(&bars[kPbHalf2], 8);
+            mbar_init(&bars[kPbTileDone], 1);
+            mbar_init(&bars[kPbDqDone], 1);
+            mbar_init(&bars[kPbAccFreeVK], kPbDrain);
+            mbar_init(&bars[kPbAccFreeQ], kPbDrain);
+            mbar_init(&bars[kPbEdgeDone], kPbEdge);
+            mbar_init(&bars[kPbVecReady], kPbAux);
+            mbar_init(&bars[kPbVecReady + 1], kPbAux);
+            mbar_init(&bars[kPbSlotFree], kPbDrain);
+            mbar_init(&bars[kPbSlotFree + 1], kPbDrain);
+            mbar_init(&bars[kPbRowA], kPbEdge);
+            mbar_init(&bars[kPbGateK0], 1);
+            mbar_init(&bars[kPbGateQD0], 1);
+            fence_barrier_init();
+            int n, h;
+            decode(0, n, h);
+            mbar_arrive_expect_tx(&bars[kPbFullK0], kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[kPbFullK0], sm_k, D + h * kHd, 0, n, kEvictFirst);
+            mbar_arrive_expect_tx(&bars[kPbFullQD0], 2 * kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[kPbFullQD0], sm_q, h * kHd, 0, n, kEvictFirst);
+            tma_load_3d(&map_do, &bars[kPbFullQD0], sm_do, h * kHd, 0, n, kEvictFirst);
+            mbar_arrive_expect_tx(&bars[kPbFullV0], kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[kPbFullV0], sm_v, 2 * D + h * kHd, 0, n, kEvictFirst);
+            mbar_arrive_expect_tx(&bars[kPbFull1], 4 * kBlkBytes);
+            tma_load_3d(&map_qkv, &bars[kPbFull1], sm_q + kBlkBytes, h * kHd, 128, n, kEvictFirst);
+            tma_load_3d(&map_do, &bars[kPbFull1], sm_do + kBlkBytes, h * kHd, 128, n, kEvictFirst);
+            tma_load_3d(&map_qkv, &bars[kPbFull1], sm_k + kBlkBytes, D + h * kHd, 128, n, kEvictFirst);
+            tma_load_3d(&map_qkv, &bars[kPbFull1], sm_v + kBlkBytes, 2 * D + h * kHd, 128, n, kEvictFirst);
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[cta_id * 32 + 30] = clock64(), p.trace[cta_id * 32 + 29] = n_my;
+
+    if (warp == 8) {
+        // ================================================================ TMA + MMA issue (one thread)
+        if (lane == 0) {
+            const uint32_t idesc_kn = umma_idesc_bf16(128, 64, 0, 1);
+            auto width = [&](int i) { return i == 0 ? 128 : w1; };
+            auto scores = [&](int j, int i) {  // S^T = K_j Q_i^T, dP^T = V_j dO_i^T
+                mma_tile_x_rows(tmem + kColST, sm_k + j * kBlkBytes, sm_q + i * kBlkBytes, width(i));
+                mma_tile_x_rows(tmem + kColDPT, sm_v + j * kBlkBytes, sm_do + i * kBlkBytes, width(i));
+                umma_commit(&bars[kPbSReady]);
+            };
+#pragma unroll 1
+            for (int it = 0; it < n_my; ++it) {
+                const uint32_t ip = it & 1;
+                const bool has_next = it + 1 < n_my;
+                int n2 = 0, h2 = 0;
+                if (has_next) decode(it + 1, n2, h2);
+                if (it == 0) {  // later items: issued behind the previous item's last gradient products (below)
+                    mbar_wait_c(&bars[kPbFullK0], 0);
+                    mbar_wait_c(&bars[kPbFullQD0], 0);
+                    mbar_wait_c(&bars[kPbFullV0], 0);
+                    tc_fence_after();
+                    scores(0, 0);
+                }
+                bool next_scores_issued = false;
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {
+                    const int g = it * 4 + b, j = b >> 1, i = b & 1;
+                    const int ksteps = width(i) >> 4;
+                    const uint8_t* do_i = sm_do + i * kBlkBytes;
+                    const uint8_t* q_i = sm_q + i * kBlkBytes;
+                    const uint8_t* dst_b = sm_dst + (b & 1) * 2 * kBlkBytes;
+                    bool fresh = (i == 0);  // first K-step of a key tile overwrites the accumulators
+                    auto grad_step = [&](int ks) {  // K-step ks = 16 queries: columns [16 ks, +16) of the block
+                        if (ks >= ksteps) return;
+                        const uint64_t db_do = umma_smem_desc_sw128(smem_u32(do_i + ks * 2048));
+                        const uint64_t db_q = umma_smem_desc_sw128(smem_u32(q_i + ks * 2048));
+                        const uint64_t da_ds = umma_smem_desc_sw128(smem_u32(dst_b + (ks >> 2) * kBlkBytes + (ks & 3) * 32));
+                        umma_f16_ts(tmem + kColDV, tmem + kColST + 64 * (ks >> 2) + 8 * (ks & 3), db_do, idesc_kn, !fresh);
+                        umma_f16(tmem + kColDK, da_ds, db_q, idesc_kn, !fresh);
+                        fresh = false;
+                    };
+                    mbar_wait_c(&bars[kPbHalf1], g & 1);
+                    if (it == kTraceItem && p.trace != nullptr) p.trace[cta_id * 32 + 20 + b] = clock64();
+                    if (i == 0) {  // dV / dK are about to be overwritten: drain number it * 2 + j - 1 must be complete
+                        const int d = it * 2 + j;
+                        if (d > 0) mbar_wait_c(&bars[kPbAccFreeVK], (d - 1) & 1);
+                    }
+                    // operand tiles of the next item whose slots are free by now
+                    if (has_next) {
+                        if (b == 3) {
+                            // K_0 / V_0 / Q_0 / dO_0 have no reader left in this item: the MMAs that read them have retired
+                            // (gates) and the edge warps have taken the edge token's dot products from every tile
+                            mbar_wait_c(&bars[kPbEdgeDone], ip);
+                            mbar_wait_c(&bars[kPbGateK0], ip);
+                            mbar_wait_c(&bars[kPbGateQD0], ip);
+                            mbar_arrive_expect_tx(&bars[kPbFullK0], kBlkBytes);
+                            tma_load_3d(&map_qkv, &bars[kPbFullK0], sm_k, D + h2 * kHd, 0, n2, kEvictFirst);
+                            mbar_arrive_expect_tx(&bars[kPbFullQD0], 2 * kBlkBytes);
+                            tma_load_3d(&map_qkv, &bars[kPbFullQD0], sm_q, h2 * kHd, 0, n2, kEvictFirst);
+                            tma_load_3d(&map_do, &bars[kPbFullQD0], sm_do, h2 * kHd, 0, n2, kEvictFirst);
+                            mbar_arrive_expect_tx(&bars[kPbFullV0], kBlkBytes);
+                            tma_load_3d(&map_qkv, &bars[kPbFullV0], sm_v, 2 * D + h2 * kHd, 0, n2, kEvictFirst);
+                        }
+                    }
+                    tc_fence_after();
+                    if (it == kTraceItem && p.trace != nullptr) p.trace[cta_id * 32 + 24 + b] = clock64();
+                    grad_step(0), grad_step(4), grad_step(1), grad_step(5);
+                    mbar_wait_c(&bars[kPbHalf2], g & 1);  // everything stored (and S^T / dP^T consumed)
+                    tc_fence_after();
+                    grad_step(2), grad_step(6), grad_step(3), grad_step(7);
+                    if (b == 2) umma_commit(&bars[kPbGateQD0]);  // Q_0 / dO_0 have no reader left in this item
+                    if (i == 1) umma_commit(&bars[kPbTileDone]);  // dV_j, dK_j complete
+                    // the next block's scores go AHEAD of dQ(b): the elementwise warps start on them while dQ(b) runs
+                    if (b == 0) {
+                        mbar_wait_c(&bars[kPbFull1], ip);  // Q_1 / dO_1 (and K_1 / V_1)
+                        tc_fence_after();
+                        scores(0, 1);
+                    } else if (b == 1) {
+                        scores(1, 0);
+                    } else if (b == 2) {
+                        scores(1, 1);
+                    } else if (has_next && mbar_test_wait(&bars[kPbFullK0], ip ^ 1) && mbar_test_wait(&bars[kPbFullQD0], ip ^ 1) &&
+                               mbar_test_wait(&bars[kPbFullV0], ip ^ 1)) {
+                        tc_fence_after();
+                        scores(0, 0);  // first block of the next item (its operands sit in the slots freed above)
+                        next_scores_issued = true;
+                    }
+                    if (b == 0 && it > 0) mbar_wait_c(&bars[kPbAccFreeQ], (it - 1) & 1);  // dQ_0 / dQ_1 of the last item drained
+                    mma_rows_t_x_cols(tmem + kColDQ + 64 * i, dst_b, sm_k + j * kBlkBytes, 8, j != 0);  // dQ_i += dS K_j
+                    if (b == 1) umma_commit(&bars[kPbGateK0]);  // dQ(b1) was the last reader of K_0
+                }
+                umma_commit(&bars[kPbDqDone]);
+                if (has_next) {
+                    if (!next_scores_issued) {
+                        mbar_wait_c(&bars[kPbFullK0], ip ^ 1);
+                        mbar_wait_c(&bars[kPbFullQD0], ip ^ 1);
+                        mbar_wait_c(&bars[kPbFullV0], ip ^ 1);
+                        tc_fence_after();
+                        scores(0, 0);
+                    }
+                    // every MMA of this item has retired: the second-half slots take the next item's tiles
+                    mbar_wait_c(&bars[kPbDqDone], ip);
+                    mbar_arrive_expect_tx(&bars[kPbFull1], 4 * kBlkBytes);
+                    tma_load_3d(&map_qkv, &bars[kPbFull1], sm_q + kBlkBytes, h2 * kHd, 128, n2, kEvictFirst);
+                    tma_load_3d(&map_do, &bars[kPbFull1], sm_do + kBlkBytes, h2 * kHd, 128, n2, kEvictFirst);
+                    tma_load_3d(&map_qkv, &bars[kPbFull1], sm_k + kBlkBytes, D + h2 * kHd, 128, n2, kEvictFirst);
+                    tma_load_3d(&map_qkv, &bars[kPbFull1], sm_v + kBlkBytes, 2 * D + h2 * kHd, 128, n2, kEvictFirst);
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ================================================================ elementwise warps: P^T and dS^T, block after block
+        const int quarter = warp & 3, phase = warp >> 2;
+        const int r = quarter * 32 + lane;  // key row in the tile == TMEM lane
+        const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int cb = 64 * phase;  // this warp's columns of every block
+#pragma unroll 1
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it & 1;
+            const float* lse2 = vec0 + 1536 * s;
+            const float* delta = lse2 + 256;
+            const bool tr = (it == kTraceItem) && warp == 0 && lane == 0 && p.trace != nullptr;
+            if (it == kTraceItem + 1 && warp == 0 && lane == 0 && p.trace != nullptr) p.trace[cta_id * 32 + 9] = clock64();
+            if (tr) p.trace[cta_id * 32 + 0] = clock64();
+            mbar_wait_c(&bars[kPbVecReady + s], (it >> 1) & 1);
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int g = it * 4 + b, j = b >> 1, i = b & 1;
+                const bool row_ok = (j * 128 + r) < nv;
+                const int width = (i == 0) ? 128 : w1;
+                const float* l2 = lse2 + i * 128;
+                const float* dl = delta + i * 128;
+                mbar_wait_c(&bars[kPbSReady], g & 1);
+                tc_fence_after();
+                if (tr) p.trace[cta_id * 32 + 1 + 2 * b] = clock64();
+                uint8_t* dst_blk = sm_dst + (b & 1) * 2 * kBlkBytes + phase * kBlkBytes;
+                uint32_t sa[16], da[16], sb[16], db[16];
+                auto finish = [&](const uint32_t(&sv)[16], const uint32_t(&dv)[16], int q) {
+                    const Cols16 o = bwd_cols16(sv, dv, l2 + cb + 16 * q, dl + cb + 16 * q, row_ok);
+                    bwd_store_ds(o, dst_blk, r, 2 * q);
+                    const uint32_t pk[8] = {o.p[0].x, o.p[0].y, o.p[0].z, o.p[0].w, o.p[1].x, o.p[1].y, o.p[1].z, o.p[1].w};
+                    tmem_st<8>(trow + kColST + cb + 8 * q, pk);
+                };
+                if (cb < width) tmem_ld<16>(trow + kColST + cb, sa), tmem_ld<16>(trow + kColDPT + cb, da);
+                tmem_wait_ld();
+                if (cb + 16 < width) tmem_ld<16>(trow + kColST + cb + 16, sb), tmem_ld<16>(trow + kColDPT + cb + 16, db);
+                if (cb < width) finish(sa, da, 0);
+                tmem_wait_ld();
+                if (cb + 32 < width) tmem_ld<16>(trow + kColST + cb + 32, sa), tmem_ld<16>(trow + kColDPT + cb + 32, da);
+                if (cb + 16 < width) finish(sb, db, 1);
+                tmem_wait_st();
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kPbHalf1]);
+                tmem_wait_ld();
+                if (cb + 48 < width) tmem_ld<16>(trow + kColST + cb + 48, sb), tmem_ld<16>(trow + kColDPT + cb + 48, db);
+                if (cb + 32 < width) finish(sa, da, 2);
+                tmem_wait_ld();
+                if (cb + 48 < width) finish(sb, db, 3);
+                tmem_wait_st();
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kPbHalf2]);
+                if (tr) p.trace[cta_id * 32 + 2 + 2 * b] = clock64();
+            }
+        }
+    } else {
+        // ================================================================ auxiliary warps: two independent groups
+        // pull the rows the preparation of item `it` reads (O, dO, lse, the edge token's q / k / v) into L2 well ahead:
+        // under load an HBM round trip is ~3000 clk
+        auto prefetch_rows = [&](int it, int first, int stride) {
+            int n, h;
+            decode(it, n, h);
+            for (int t = first; t <= nv; t += stride) {
+                const size_t off = (static_cast<size_t>(n) * p.T + t) * D + h * kHd;
+                prefetch_l2(p.out + off);
+                prefetch_l2(p.d_out + off);
+            }
+            if (first < 3) prefetch_l2(p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + first * D + h * kHd);
+            if (first < 9) prefetch_l2(p.lse + (static_cast<size_t>(n) * p.heads + h) * p.T + first * 32);
+        };
+        if (warp < 9 + kPbEdge) {
+            // ------------------------------------------------------------ edge warps
+            const int ew = warp - 9;         // 0..2
+            const int el = ew * 32 + lane;   // 0..95
+            // lse2 and the edge token's vectors / scalars of item `it` into its slot (global memory only)
+            auto prepare_vectors = [&](int it) {
+                const int s = it & 1;
+                int n, h;
+                decode(it, n, h);
+                float* lse2 = vec0 + 1536 * s;
+                float* qx = x0 + kPbXFloats * s;
+                float* kx = qx + 64;
+                float* vx = qx + 128;
+                float* dox = qx + 192;
+                float* scal = qx + 256;
+                const size_t vbase = (static_cast<size_t>(n) * p.heads + h) * p.T;
+                const size_t rowx = static_cast<size_t>(n) * p.T + nv;
+                const bf16* xq = p.qkv + rowx * 3 * D + h * kHd;
+                uint32_t e0 = 0, e1 = 0, e2 = 0;
+                float lse_x = 0.f, l[3];
+                if (ew == 0) {
+                    e0 = *reinterpret_cast<const uint32_t*>(xq + 2 * lane);                              // q_x
+                    e1 = *reinterpret_cast<const uint32_t*>(p.d_out + rowx * D + h * kHd + 2 * lane);    // dO_x
+                    e2 = *reinterpret_cast<const uint32_t*>(p.out + rowx * D + h * kHd + 2 * lane);      // O_x
+                    lse_x = p.lse[vbase + nv];
+                } else if (ew == 1) {
+                    e0 = *reinterpret_cast<const uint32_t*>(xq + D + 2 * lane);                          // k_x
+                } else {
+                    e0 = *reinterpret_cast<const uint32_t*>(xq + 2 * D + 2 * lane);                      // v_x
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) l[u] = (el + 96 * u < nv) ? p.lse[vbase + el + 96 * u] : INFINITY;
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+                    if (el + 96 * u < 256) lse2[el + 96 * u] = l[u] * kLog2e;
+                if (ew == 0) {
+                    qx[2 * lane] = bf_lo(e0), qx[2 * lane + 1] = bf_hi(e0);
+                    dox[2 * lane] = bf_lo(e1), dox[2 * lane + 1] = bf_hi(e1);
+                    const float dx = warp_sum(fmaf(bf_lo(e2), bf_lo(e1), bf_hi(e2) * bf_hi(e1)));
+                    if (lane == 0) scal[2] = lse_x * kLog2e, scal[3] = dx;
+                } else if (ew == 1) {
+                    kx[2 * lane] = bf_lo(e0), kx[2 * lane + 1] = bf_hi(e0);
+                } else {
+                    vx[2 * lane] = bf_lo(e0), vx[2 * lane + 1] = bf_hi(e0);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kPbVecReady + s]);
+            };
+            prepare_vectors(0);
+#pragma unroll 1
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it & 1;
+                const uint32_t ip = it & 1;
+                int n, h;
+                decode(it, n, h);
+                float* lse2 = vec0 + 1536 * s;
+                float* delta = lse2 + 256;
+                float* pcol = lse2 + 512;    // p(query i, key x)
+                float* dscol = lse2 + 768;   // ds(query i, key x)
+                float* prow = lse2 + 1024;   // p(query x, key r)
+                float* dsrow = lse2 + 1280;  // ds(query x, key r)
+                float* qx = x0 + kPbXFloats * s;
+                float* kx = qx + 64;
+                float* vx = qx + 128;
+                float* dox = qx + 192;
+                float* scal = qx + 256;  // [0] p_xx, [1] ds_xx, [2] lse2_x, [3] delta_x
+                const bool tr = (it == kTraceItem) && ew == 0 && lane == 0 && p.trace != nullptr;
+                if (tr) p.trace[cta_id * 32 + 10] = clock64();
+                if (it + 1 < n_my) prefetch_rows(it + 1, el, 96);
+                mbar_wait_c(&bars[kPbVecReady + s], (it >> 1) & 1);  // lse2, delta (drain warps), edge vectors
+                // edge token x = nv: row x (query x against every key) and column x (key x against every query).  Key tile
+                // 0's part of row x comes first and is announced on its own: the drain of dV_0 / dK_0 needs nothing else.
+                const float lse2_x = scal[2], delta_x = scal[3];
+                mbar_wait_c(&bars[kPbFullK0], ip);
+                mbar_wait_c(&bars[kPbFullV0], ip);
+                if (tr) p.trace[cta_id * 32 + 11] = clock64();
+#pragma unroll 1
+                for (int t = el; t < 128; t += 96) {
+                    const float pr = exp2f(fmaf(row_dot(sm_k, t, qx), kLog2e, -lse2_x));
+                    prow[t] = pr, dsrow[t] = pr * (row_dot(sm_v, t, dox) - delta_x);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kPbRowA]);
+                mbar_wait_c(&bars[kPbFullQD0], ip);
+#pragma unroll 1
+                for (int t = el; t < 128; t += 96) {
+                    const float pc = exp2f(fmaf(row_dot(sm_q, t, kx), kLog2e, -lse2[t]));
+                    pcol[t] = pc, dscol[t] = pc * (row_dot(sm_do, t, vx) - delta[t]);
+                }
+                mbar_wait_c(&bars[kPbFull1], ip);
+#pragma unroll 1
+                for (int t = 128 + el; t < 256; t += 96) {
+                    float pr = 0.f, dsr = 0.f, pc = 0.f, dsc = 0.f;
+                    if (t < nv) {
+                        pr = exp2f(fmaf(row_dot(sm_k, t, qx), kLog2e, -lse2_x));
+                        dsr = pr * (row_dot(sm_v, t, dox) - delta_x);
+                        pc = exp2f(fmaf(row_dot(sm_q, t, kx), kLog2e, -lse2[t]));
+                        dsc = pc * (row_dot(sm_do, t, vx) - delta[t]);
+                    }
+                    prow[t] = pr, dsrow[t] = dsr, pcol[t] = pc, dscol[t] = dsc;
+                }
+                if (ew == 2) {  // q_x . k_x and dO_x . v_x (two elements per lane)
+                    const float sxx = warp_sum(fmaf(qx[2 * lane], kx[2 * lane], qx[2 * lane + 1] * kx[2 * lane + 1]));
+                    const float dpxx = warp_sum(fmaf(dox[2 * lane], vx[2 * lane], dox[2 * lane + 1] * vx[2 * lane + 1]));
+                    const float pxx = exp2f(fmaf(sxx, kLog2e, -lse2_x));
+                    if (lane == 0) scal[0] = pxx, scal[1] = pxx * (dpxx - delta_x);
+                }
+                named_bar_sync(3, kPbEdge * 32);  // the edge warps: row / column vectors and scalars complete
+                if (tr) p.trace[cta_id * 32 + 13] = clock64();
+                bf16* gx = p.d_qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd;
+                if (ew == 0) edge_gemv(pcol, sm_do, nv, scal[0], dox, gx + 2 * D, 1.0f, lane);  // dV_x
+                if (ew == 1) edge_gemv(dscol, sm_q, nv, scal[1], qx, gx + D, 1.0f, lane);       // dK_x
+                if (ew == 2) edge_gemv(dsrow, sm_k, nv, scal[1], kx, gx, 1.0f, lane);           // dQ_x
+                __syncwarp();
+                // the operand tiles are no longer read from here, and the drain warps may use this item's vectors
+                if (lane == 0) mbar_arrive(&bars[kPbEdgeDone]);
+                if (tr) p.trace[cta_id * 32 + 12] = clock64();
+                // the next item's vectors go into the other slot once the drain warps are done with its last user
+                if (it + 1 < n_my) {
+                    if (it >= 1) mbar_wait_c(&bars[kPbSlotFree + (s ^ 1)], ((it - 1) >> 1) & 1);
+                    prepare_vectors(it + 1);
+                }
+            }
+        } else {
+            // ------------------------------------------------------------ drain warps
+            const int dw = warp - 9 - kPbEdge;  // 0..3
+            const int quarter = warp & 3;        // tensor-memory lane quarter this warp may read (12..15 -> 0..3)
+            const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+            // delta = rowsum(dO * O) of item `it` into its slot: eight lanes share a 128-byte row, four rows per step,
+            // 16 steps per warp in two batches of eight loads in flight
+            auto prepare_delta = [&](int it) {
+                const int s = it & 1;
+                int n, h;
+                decode(it, n, h);
+                float* delta = vec0 + 1536 * s + 256;
+#pragma unroll 1
+                for (int base = 0; base < 16; base += 8) {
+                    uint4 xo[8], xd[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int row = dw * 64 + (base + u) * 4 + (lane >> 3);
+                        const size_t off = (static_cast<size_t>(n) * p.T + min(row, nv)) * D + h * kHd + (lane & 7) * 8;
+                        xo[u] = *reinterpret_cast<const uint4*>(p.out + off);
+                        xd[u] = *reinterpret_cast<const uint4*>(p.d_out + off);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int row = dw * 64 + (base + u) * 4 + (lane >> 3);
+                        float d = chunk_dot(xo[u], xd[u]);
+                        d += __shfl_xor_sync(0xffffffffu, d, 1);
+                        d += __shfl_xor_sync(0xffffffffu, d, 2);
+                        d += __shfl_xor_sync(0xffffffffu, d, 4);
+                        if ((lane & 7) == 0) delta[row] = (row < nv) ? d : 0.f;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kPbVecReady + s]);
+            };
+            prepare_delta(0);
+#pragma unroll 1
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it & 1;
+                const uint32_t ip = it & 1;
+                int n, h;
+                decode(it, n, h);
+                const float* lse2 = vec0 + 1536 * s;
+                const float* dscol = lse2 + 768;
+                const float* prow = lse2 + 1024;
+                const float* dsrow = lse2 + 1280;
+                const float* qx = x0 + kPbXFloats * s;
+                const float* kx = qx + 64;
+                const float* dox = qx + 192;
+                const bool tr = (it == kTraceItem) && dw == 0 && lane == 0 && p.trace != nullptr;
+                // the next item's delta into the other slot (its last readers, the elementwise warps of the previous
+                // item and this warp's own drains, are done)
+                if (it + 1 < n_my) prepare_delta(it + 1);
+                if (tr) p.trace[cta_id * 32 + 16] = clock64();
+                bf16* gd = p.d_qkv + static_cast<size_t>(n) * p.T * 3 * D + h * kHd;
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    mbar_wait_c(&bars[kPbTileDone], (it * 2 + j) & 1);
+                    // key tile 0 needs the first half of the edge row; everything after it the whole edge phase
+                    mbar_wait_c(&bars[j == 0 ? kPbRowA : kPbEdgeDone], ip);
+                    tc_fence_after();
+                    if (tr) p.trace[cta_id * 32 + 14 + 4 * j] = clock64();
+                    const int row0 = j * 128 + quarter * 32;
+#pragma unroll 1
+                    for (int ph = 0; ph < 2; ++ph)
+                        bwd_epilogue2(trow + kColDV + ph * 32, prow[row0 + lane], dox + ph * 32, gd + 2 * D + ph * 32, row0,
+                                      trow + kColDK + ph * 32, dsrow[row0 + lane], qx + ph * 32, gd + D + ph * 32, row0, lane,
+                                      static_cast<size_t>(3) * D, nv);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[kPbAccFreeVK]);
+                    if (tr) p.trace[cta_id * 32 + 15 + 4 * j] = clock64();
+                }
+                mbar_wait_c(&bars[kPbDqDone], ip);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ph = 0; ph < 2; ++ph)
+                    bwd_epilogue2(trow + kColDQ + ph * 32, dscol[quarter * 32 + lane], kx + ph * 32, gd + ph * 32, quarter * 32,
+                                  trow + kColDQ + 64 + ph * 32, dscol[128 + quarter * 32 + lane], kx + ph * 32, gd + ph * 32,
+                                  128 + quarter * 32, lane, static_cast<size_t>(3) * D, nv);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kPbAccFreeQ]), mbar_arrive(&bars[kPbSlotFree + s]);
+                if (tr) p.trace[cta_id * 32 + 17] = clock64();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[cta_id * 32 + 31] = clock64();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // backward, long sequences (T > 257: ViT-L/14 @336)
 // ---------------------------------------------------------------------------------------------------------
@@ -2199,6 +2768,11 @@ bool g_fwd_persist = []() {
     return !(e != nullptr && e[0] == '0');
 }();
 
+bool g_bwd_persist = []() {
+    const char* e = getenv("PCG_ATTN_PERSIST");
+    return !(e != nullptr && e[0] == '0');
+}();
+
 bool g_force_legacy = []() {
     const char* e = getenv("PCG_ATTN_LEGACY");
     return e != nullptr && e[0] == '1';
@@ -2214,8 +2788,11 @@ extern "C" int pcg_attn_set_legacy(int on) {  // test hook: force the mma.sync k
     return 0;
 }
 
-extern "C" int pcg_attn_set_persist(int on) {  // test / benchmark hook: persistent (1) or one-shot (0) tcgen05 kernels
-    g_fwd_persist = on != 0;
+// test / benchmark hook: 0 one-tile-per-CTA tcgen05 kernels, 1 persistent forward + backward (the default), 2 persistent
+// backward only, 3 persistent forward only
+extern "C" int pcg_attn_set_persist(int mode) {
+    g_fwd_persist = mode == 1 || mode == 3;
+    g_bwd_persist = mode == 1 || mode == 2;
     return 0;
 }
 
@@ -2330,9 +2907,20 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
     CUtensorMap map, map_do;
     if (int rc = make_map3(&map, qkv, n, T, 3 * D)) return rc;
     if (int rc = make_map3(&map_do, d_out, n, T, D)) return rc;
+    const int nv = T - 1;
+    if (g_bwd_persist && nv > 128) {  // two key tiles: the persistent kernel (a single tile keeps the one-shot kernel)
+        static PerDeviceOnce persist_configured;
+        PCG_ONCE_PER_DEVICE(persist_configured, PCG_CUDA(cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbSmemBytes)));
+        const long long items = static_cast<long long>(n) * heads;
+        PbParams pb{T, heads, nv, static_cast<int>(items), static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
+                    static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace};
+        const int grid = static_cast<int>(std::min<long long>(items, sm_count()));
+        attn_bwd_persist_kernel<<<grid, kPbThreads, kPbSmemBytes, s>>>(map, map_do, pb);
+        PCG_LAUNCH_CHECK("attn_bwd_persist_kernel");
+        return 0;
+    }
     static PerDeviceOnce configured;
     PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes)));
-    const int nv = T - 1;
     BwdParams p{T,   heads, nv, (nv + 127) / 128, static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
                 static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace, sm_count(), g_bwd_stagger};  // delta: in-kernel
     attn_bwd_tc_kernel<<<dim3(heads, n), kBwdThreads, kBwdSmemBytes, s>>>(map, map_do, p);

@@ -15,7 +15,7 @@ def main():
     ap.add_argument("--t", type=int, default=257)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent CTAs")
+    ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent fwd+bwd, 2: persistent bwd only, 3: persistent fwd only")
     args = ap.parse_args()
     native.lib().pcg_attn_set_persist(args.persist)
     dev = torch.device("cuda", 0)

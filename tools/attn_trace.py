@@ -17,6 +17,14 @@ FWD2 = {0: "item start", 9: "next item start", 4: "S ready", 5: "max pass done",
         21: "edge: K landed", 22: "edge: K dots done", 23: "edge: row done"}
 FWD = {0: "start", 1: "setup done", 2: "K+Q landed", 3: "V landed", 4: "S ready (w0)", 5: "max pass done", 6: "exp pass done",
        7: "O ready", 8: "epilogue done", 9: "edge row done", 10: "all warps done"}
+# persistent backward: warp 0's stamps of one steady-state item
+BWD2 = {0: "item start (vectors wait)", 1: "b0 S/dP ready", 2: "b0 alu done", 3: "b1 S/dP ready", 4: "b1 alu done",
+        5: "b2 S/dP ready", 6: "b2 alu done", 7: "b3 S/dP ready", 8: "b3 alu done", 9: "next item start",
+        10: "edge: item start", 11: "edge: tiles landed", 13: "edge: dots done", 12: "edge: gemv done (EdgeDone)",
+        16: "drain: next delta prepared", 14: "drain: tile0 complete seen", 15: "drain: dV0/dK0 drained",
+        18: "drain: tile1 complete seen", 19: "drain: dV1/dK1 drained", 17: "drain: dQ drained", 20: "ctl: b0 half1 seen", 21: "ctl: b1 half1 seen",
+        22: "ctl: b2 half1 seen", 23: "ctl: b3 half1 seen", 24: "ctl: b0 grads issue", 25: "ctl: b1 grads issue",
+        26: "ctl: b2 grads issue", 27: "ctl: b3 grads issue"}
 BWD = {0: "start", 1: "first loads landed", 2: "edge vectors ready", 3: "edge gemv done", 4: "b0 S/dP ready", 5: "b0 alu done",
        6: "b1 S/dP ready", 7: "b1 alu done", 8: "b2 S/dP ready", 9: "b2 alu done", 10: "b3 S/dP ready", 11: "b3 alu done",
        12: "tile0 mma done", 13: "tile1 mma done", 14: "epilogues done", 15: "all warps done", 16: "ctl b0 P/dS seen",
@@ -44,7 +52,7 @@ def main():
     ap.add_argument("--t", type=int, default=257)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--iters", type=int, default=8)
-    ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent CTAs")
+    ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent fwd+bwd, 2: persistent bwd only, 3: persistent fwd only")
     args = ap.parse_args()
     native.lib().pcg_attn_set_persist(args.persist)
     dev = torch.device("cuda", 0)
@@ -77,18 +85,27 @@ def main():
     native.lib().pcg_attn_set_trace(trace.data_ptr())
     out, lse = ops.attn_fwd(qkv, n, t, h)
     torch.cuda.synchronize()
-    if args.persist:
+    if args.persist in (1, 3):
         tt = trace.cpu().double()
         tt = tt[tt[:, 30] > 0]
         life = tt[:, 31] - tt[:, 30]
         print(f"persistent forward: {tt.shape[0]} CTAs, items per CTA {tt[:, 29].min():.0f}-{tt[:, 29].max():.0f}, CTA lifetime "
               f"median {life.median():.0f} max {life.max():.0f} clk, per item {float((life / tt[:, 29]).median()):.0f} clk")
-    show(trace, FWD2 if args.persist else FWD, "forward (persistent, one steady-state item of each CTA)" if args.persist else "forward")
+    show(trace, FWD2 if args.persist in (1, 3) else FWD,
+         "forward (persistent, one steady-state item of each CTA)" if args.persist in (1, 3) else "forward")
     trace.zero_()
     ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
     torch.cuda.synchronize()
     native.lib().pcg_attn_set_trace(None)
-    show(trace[: h * n], BWD, "backward")
+    if args.persist in (1, 2) and t >= 130:
+        tt = trace.cpu().double()
+        tt = tt[tt[:, 30] > 0]
+        life = tt[:, 31] - tt[:, 30]
+        print(f"persistent backward: {tt.shape[0]} CTAs, items per CTA {tt[:, 29].min():.0f}-{tt[:, 29].max():.0f}, CTA lifetime "
+              f"median {life.median():.0f} max {life.max():.0f} clk, per item {float((life / tt[:, 29]).median()):.0f} clk")
+        show(trace, BWD2, "backward (persistent, one steady-state item of each CTA)")
+    else:
+        show(trace[: h * n], BWD, "backward")
 
 
 if __name__ == "__main__":
