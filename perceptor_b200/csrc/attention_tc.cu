@@ -847,6 +847,12 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kB2TmemFree]);
+            // Rows go straight to global memory from the tensor-memory layout (thread = row: eight 16-byte stores cover
+            // the row's 128 contiguous bytes, one full line).  The one-shot kernel stages the tile through shared memory
+            // for row-coalesced stores; here that round trip (store -> sync -> load -> store) sits on the per-item chain
+            // and costs more than the extra store transactions.
+            bf16* grow = p.out + (static_cast<size_t>(n) * p.T + q0 + r) * D + h * kHd;
+            const bool row_ok = q0 + r < nv;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const float4 xa = *reinterpret_cast<const float4*>(vx + g * 8);
@@ -859,24 +865,11 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
                                                      fmaf(px, xb.y, __uint_as_float(v[8 * g + 5])) * inv),
                                            pack_bf16(fmaf(px, xb.z, __uint_as_float(v[8 * g + 6])) * inv,
                                                      fmaf(px, xb.w, __uint_as_float(v[8 * g + 7])) * inv));
-                *reinterpret_cast<uint4*>(sm_q + row_chunk(r, g)) = o;
+                if (row_ok) *reinterpret_cast<uint4*>(grow + g * 8) = o;
             }
-            __syncwarp();
-            bf16* gout = p.out + static_cast<size_t>(n) * p.T * D + h * kHd;
-            // Pull the staged rows back into registers, hand the Q slot back to the TMA unit, then store.  (The reads
-            // have returned this warp's own staging writes, so those are performed; a fence.proxy.async here would
-            // compile to MEMBAR.ALL.CTA and sit behind the global stores for ~1500 clk.)
-            uint4 st[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                st[i] = *reinterpret_cast<const uint4*>(sm_q + row_chunk(warp * 32 + i * 4 + (lane >> 3), lane & 7));
+            // this item's Q slot and edge vectors (v_x above was their last reader in this warp) may be refilled
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kB2Done + s]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = warp * 32 + i * 4 + (lane >> 3), ch = lane & 7;
-                if (q0 + row < nv) *reinterpret_cast<uint4*>(gout + static_cast<size_t>(q0 + row) * D + ch * 8) = st[i];
-            }
             if (tr) p.trace[cta_id * 32 + 8] = clock64();
         }
     } else {
