@@ -36,13 +36,17 @@ WORKLOADS = {
     # BASELINE configs[3] as written: ONE 768x768 image, 256 cutouts in total, sharded over the ranks (strong scaling)
     "vit_l14_336_256cut_768px_1image": ("ViT-L-14-336", 768, 256, 192, 0),
     "vit_b32_224_16cut_256px": ("ViT-B-32", 256, 16, 64, 1),
+    # one rank's share of the strong-scaling record at 8 GPUs (16 of the 128 cutouts), as a single-GPU proxy for tuning
+    "vit_l14_224_16cut_512px": ("ViT-L-14", 512, 16, 128, 1),
 }
 DEFAULT_WORKLOAD = "vit_l14_224_128cut_512px"
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05_kernel launch, mean over the eight GEMM
 # shapes of one transformer layer (forward qkv / out / fc / proj, backward dproj / dfc / dout / dqkv), READ from the
 # committed `ncu --set full` summaries (tools/ncu_summ.py output) rather than typed in.
-NCU_GEMM_TRAFFIC_FILES = {"vit_l14_224_128cut_512px": ("profiles/r01d_gemm_fwd_ncu_full.csv",
-                                                       "profiles/r01d_gemm_bwd_ncu_full.csv")}
+# (file, first GEMM row, rows): profiles/r02_gemm_ncu_full.csv holds 16 consecutive GEMM launches around the forward /
+# backward turn of a step (tools/profile_r02.sh); rows 3..10 are exactly one layer's eight shapes (qkv, out, fc, proj,
+# dproj, dfc, dout, dqkv)
+NCU_GEMM_TRAFFIC_FILES = {"vit_l14_224_128cut_512px": (("profiles/r02_gemm_ncu_full.csv", 3, 8),)}
 
 
 def ncu_gemm_traffic(workload: str):
@@ -52,7 +56,7 @@ def ncu_gemm_traffic(workload: str):
     if not files:
         return None, "no ncu capture committed for this workload"
     vals = []
-    for rel in files:
+    for rel, first, count in files:
         path = os.path.join(ROOT, rel)
         if not os.path.exists(path):
             return None, f"{rel} missing"
@@ -62,13 +66,15 @@ def ncu_gemm_traffic(workload: str):
         ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         units = rows[1]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        mine = []
         for r in rows[2:]:
             if len(r) > max(ri, wi) and "gemm_tcgen05_kernel" in r[ki]:
-                vals.append(float(r[ri].replace(",", "")) * scale.get(units[ri], 1.0)
+                mine.append(float(r[ri].replace(",", "")) * scale.get(units[ri], 1.0)
                             + float(r[wi].replace(",", "")) * scale.get(units[wi], 1.0))
+        vals += mine[first:first + count]
     if not vals:
         return None, "no gemm_tcgen05_kernel rows in the ncu summaries"
-    return sum(vals) / len(vals), f"mean of {len(vals)} captured launches in {', '.join(files)}"
+    return sum(vals) / len(vals), f"mean of {len(vals)} captured launches (one layer's eight shapes) in {', '.join(f[0] for f in files)}"
 METRIC = "CLIP-guidance cutouts/sec (loss + image grad), ViT-L/14, at 1/2/4/8 B200"
 
 

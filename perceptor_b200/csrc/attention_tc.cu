@@ -1637,8 +1637,7 @@ constexpr int kPbEdge = 3;   // edge warps 9..11: the edge token's row and colum
 constexpr int kPbDrain = 4;  // drain warps 12..15 (lane quarters 0..3): accumulator epilogues, next item's delta
 constexpr int kPbAux = kPbEdge + kPbDrain;  // 16 warps = 4 per scheduler: 128 registers (a 17th caps the kernel at 96)
 constexpr int kPbThreads = (9 + kPbAux) * 32;
-constexpr int kPbOffStage = 12 * kBlkBytes;               // 4 drain warps x [32 rows x 64 B] (+ 3 unused slices)
-constexpr int kPbOffVec = kPbOffStage + kPbAux * 2048;         // 2 slots x float[256] x 6: lse2, delta, pcol, dscol, prow, dsrow
+constexpr int kPbOffVec = 12 * kBlkBytes;                 // 2 slots x float[256] x 6: lse2, delta, pcol, dscol, prow, dsrow
 constexpr int kPbOffX = kPbOffVec + 2 * 6 * 1024;         // 2 slots x {float[64] x 4: q_x, k_x, v_x, dO_x; 8 scalars}
 constexpr int kPbXFloats = 4 * 64 + 8;
 constexpr int kPbOffBar = kPbOffX + 2 * kPbXFloats * 4;
@@ -1930,7 +1929,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
                 prefetch_l2(p.d_out + off);
             }
             if (first < 3) prefetch_l2(p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + first * D + h * kHd);
-            if (first < 9) prefetch_l2(p.lse + (static_cast<size_t>(n) * p.heads + h) * p.T + first * 32);
+            if (first < 9) prefetch_l2(p.lse + (static_cast<size_t>(n) * p.heads + h) * p.T + min(first * 32, nv));
         };
         if (warp < 9 + kPbEdge) {
             // ------------------------------------------------------------ edge warps
@@ -2905,6 +2904,7 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
         static PerDeviceOnce persist_configured;
         PCG_ONCE_PER_DEVICE(persist_configured, PCG_CUDA(cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbSmemBytes)));
         const long long items = static_cast<long long>(n) * heads;
+        PCG_CHECK_ARG(items < (1ll << 30), "pcg_attn_bwd: too many (cutout, head) items");
         PbParams pb{T, heads, nv, static_cast<int>(items), static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
                     static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace};
         const int grid = static_cast<int>(std::min<long long>(items, sm_count()));
