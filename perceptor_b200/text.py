@@ -9,9 +9,9 @@ Mirrors
     `ftfy.fix_text` call of basic_clean (:60-63) is applied only when ftfy is importable.
   * the text transformer restated at perceptor/models/ruclip/model.py:165-228: token + positional embedding ->
     pre-LN residual attention blocks under a causal mask -> ln_final -> the end-of-text position @ text_projection.
-The merge table (`bpe_simple_vocab_16e6.txt.gz`, 1.3 MB: OpenAI CLIP's published vocabulary, MIT licence) ships as
-package data (perceptor_b200/data/, see its README) so that `add_texts_` works out of the box; `bpe_path=` or
-PCG_BPE_VOCAB select another table.
+The 48 894 merge rules the tokenizer uses (the head of OpenAI CLIP's published `bpe_simple_vocab_16e6.txt`, MIT
+licence) ship as package data (perceptor_b200/data/clip_bpe_merges.txt.gz, see the README there) so that `add_texts_`
+works out of the box; `bpe_path=` or PCG_BPE_VOCAB select another table (the full original file works as well).
 """
 from __future__ import annotations
 
@@ -30,7 +30,7 @@ try:  # pragma: no cover - optional dependency of the reference's basic_clean
 except ImportError:  # pragma: no cover
     ftfy = None
 
-DEFAULT_VOCAB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "bpe_simple_vocab_16e6.txt.gz")
+DEFAULT_VOCAB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "clip_bpe_merges.txt.gz")
 SOT, EOT = "<|startoftext|>", "<|endoftext|>"
 N_MERGES = 49152 - 256 - 2
 _PATTERN = re.compile(r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""",
@@ -59,7 +59,7 @@ class SimpleTokenizer:
         if not os.path.exists(bpe_path):
             raise FileNotFoundError(
                 f"the CLIP BPE merge table {bpe_path} does not exist: pass bpe_path= or set PCG_BPE_VOCAB (the packaged "
-                "copy is perceptor_b200/data/bpe_simple_vocab_16e6.txt.gz), or add precomputed encodings with "
+                "copy is perceptor_b200/data/clip_bpe_merges.txt.gz), or add precomputed encodings with "
                 "add_encodings_()")
         opener = gzip.open if str(bpe_path).endswith(".gz") else open
         with opener(bpe_path, "rb") as f:
