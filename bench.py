@@ -397,6 +397,41 @@ def run_native(args, rank: int, world: int, local_rank: int):
                   "note": "one 512x512 image, 128 cutouts sharded over the ranks, image gradient + loss all-reduced; "
                           "device-timed, max over ranks, CUDA-graph replay"}
 
+    # The other BASELINE.json configs on ONE GPU, as short sub-records beside the headline (they are parity-test cases
+    # first; these lines only put a driver-run number next to each): configs[0] shape, configs[1], configs[3] shape.
+    others = None
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_other_configs:
+        others = {}
+        del loss_mod, eng  # frees the 19 GB activation slot of the headline workload (the encoder itself is memoised)
+        torch.cuda.empty_cache()
+        for tag, wl, o_steps in (("configs[0] shape on the GPU", "vit_b32_224_16cut_256px", 20),
+                                 ("configs[1]", "vit_b32_224_64cut_4x512px", 20),
+                                 ("configs[3] shape on one GPU", "vit_l14_336_256cut_768px", 3)):
+            o_arch, o_hw, o_cut, o_min, o_imgs = WORKLOADS[wl]
+            o_mod = losses.CLIP(o_arch, n_cutouts=o_cut, min_size=o_min, max_size=o_hw, seed=0)
+            o_mod.add_encodings_(torch.randn(2, SHAPES[o_arch].embed, generator=torch.Generator().manual_seed(0)))
+            o_mod.model.engine().prebuild_tables(o_min, o_hw)
+            o_images = torch.rand(o_imgs, 3, o_hw, o_hw, generator=torch.Generator().manual_seed(0)).to(device)
+
+            def step_other():
+                img = o_images.detach().requires_grad_()
+                loss = o_mod(img)
+                loss.backward()
+                return loss
+
+            for _ in range(3):
+                step_other()
+            o_ms = timed(step_other, o_steps) / o_steps
+            others[wl] = {"baseline_config": tag, "model": o_arch, "images": o_imgs, "image": f"{o_hw}x{o_hw}",
+                          "cutouts_per_step": o_imgs * o_cut, "steps": o_steps, "ms_per_step": o_ms,
+                          "value": o_imgs * o_cut / (o_ms * 1e-3), "unit": "cutouts/s",
+                          "frac_of_sustained_peak": o_imgs * o_cut / (o_ms * 1e-3) * SHAPES[o_arch].flops_per_cutout()
+                          / 1e12 / measured_peaks()["bf16_tflops_sustained"]}
+            del o_mod, o_images
+            torch.cuda.empty_cache()
+        loss_mod = losses.CLIP(arch, n_cutouts=n_cut, min_size=min_size, max_size=hw, seed=0)  # for the parity field
+        loss_mod.add_encodings_(target_enc)
+
     if rank != 0:
         return
     parity = parity_check(loss_mod, arch, shape, hw, min_size, device) if not args.no_parity else None
@@ -443,6 +478,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
     }
     if strong is not None:
         line["strong"] = strong
+    if others:
+        line["other_configs"] = others
     if parity is not None:
         line["parity"] = parity
     if cpu_value is not None:
@@ -464,6 +501,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8, help="cutouts per CPU-baseline step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short sub-records of the other BASELINE configs (N = 1, default workload)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check against the CPU oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
