@@ -372,6 +372,26 @@ def run_native(args, rank: int, world: int, local_rank: int):
     e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
     e2e_value = cutouts_per_step / (e2e_ms * 1e-3)
 
+    # The same workload with the LAST block run in full (every token through its out-projection / MLP, as the reference's
+    # dense computation does) instead of on the class-token rows the loss reads: outputs are the same, 3.3 % more FLOPs.
+    pooled = bool(lib.pcg_set_pooled_last_block(1))
+    lib.pcg_set_pooled_last_block(int(pooled))
+    full_last = None
+    if pooled and world == 1 and not args.no_full_last_block:
+        lib.pcg_set_pooled_last_block(0)
+        eng._slot = eng._slot_key = None  # captured graphs keep the sequence they were captured with
+        try:
+            for _ in range(3):
+                step_device()
+            f_ms = timed(step_device, args.steps) / args.steps
+        finally:
+            lib.pcg_set_pooled_last_block(1)
+            eng._slot = eng._slot_key = None
+        full_last = {"ms_per_step": f_ms, "value": cutouts_per_step / (f_ms * 1e-3), "unit": "cutouts/s",
+                     "steps": args.steps,
+                     "note": "PCG_FULL_LAST_BLOCK=1: all n*T rows through the last block's attention, out-projection, "
+                             "ln_2 and MLP (what the reference computes and then discards); same loss and gradient"}
+
     # strong-scaling sub-record of the headline workload (C3 at B = 1): ONE image, the same 128 cutouts
     # split over the ranks, gradient all-reduced.  Every rank runs it; at N = 1 it is the main measurement itself.
     strong = None
@@ -425,8 +445,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
             others[wl] = {"baseline_config": tag, "model": o_arch, "images": o_imgs, "image": f"{o_hw}x{o_hw}",
                           "cutouts_per_step": o_imgs * o_cut, "steps": o_steps, "ms_per_step": o_ms,
                           "value": o_imgs * o_cut / (o_ms * 1e-3), "unit": "cutouts/s",
-                          "frac_of_sustained_peak": o_imgs * o_cut / (o_ms * 1e-3) * SHAPES[o_arch].flops_per_cutout()
-                          / 1e12 / measured_peaks()["bf16_tflops_sustained"]}
+                          "frac_of_sustained_peak": o_imgs * o_cut / (o_ms * 1e-3)
+                          * SHAPES[o_arch].flops_per_cutout(pooled_last_block=pooled) / 1e12 / measured_peaks()["bf16_tflops_sustained"]}
             del o_mod, o_images
             torch.cuda.empty_cache()
         loss_mod = losses.CLIP(arch, n_cutouts=n_cut, min_size=min_size, max_size=hw, seed=0)  # for the parity field
@@ -436,8 +456,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
         return
     parity = parity_check(loss_mod, arch, shape, hw, min_size, device) if not args.no_parity else None
     peaks = measured_peaks()
-    flops_per_cutout = shape.flops_per_cutout()
+    flops_per_cutout = shape.flops_per_cutout(pooled_last_block=pooled)  # what the step executes
     step_tflops = value / world * flops_per_cutout / 1e12
+    model_tflops = value / world * shape.flops_per_cutout() / 1e12       # the reference's dense op count at this speed
     gemm = prof["gemm"]
     gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
@@ -460,7 +481,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
                    "weights": "random-init (no network for checkpoints)",
                    "l2": "per-step working set (activation stash >= 19 GB for ViT-L/14 x128) >> 126 MB L2; no flush needed",
                    "launch": "CUDA-graph replay (forward graph + backward graph)" if graphs_on else "eager launches",
+                   "last_block": ("class-token rows only after the K/V projection (the loss reads nothing else); "
+                                  "FLOPs below are the EXECUTED ones" if pooled else "full"),
                    "step_tflops_per_gpu": step_tflops, "step_frac_of_peak": step_tflops / peak,
+                   "step_dense_model_tflops_per_gpu": model_tflops,
                    "kernel_families": families},
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "cutouts/s", "ms_per_step": e2e_ms,
@@ -476,6 +500,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
                      "timing": "CUDA event pair around every launch, second pass over the same K steps "
                                f"({prof_ms / args.steps:.2f} ms/step with the events, eager launches)"},
     }
+    if full_last is not None:
+        line["full_last_block"] = full_last
     if strong is not None:
         line["strong"] = strong
     if others:
@@ -503,6 +529,8 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short sub-records of the other BASELINE configs (N = 1, default workload)")
+    ap.add_argument("--no-full-last-block", action="store_true",
+                    help="skip the sub-record with the last block run on all tokens (N = 1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check against the CPU oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PCG_ABI_VERSION 3
+#define PCG_ABI_VERSION 4
 
 enum { PCG_ACT_QUICKGELU = 0, PCG_ACT_GELU = 1 };
 
@@ -132,6 +132,12 @@ int pcg_layernorm_fwd(const float *x, const float *gamma, const float *beta, voi
  * (10 instead of 16 bytes per element; what pcg_guidance_bwd uses). */
 int pcg_layernorm_bwd(const void *dy_bf16, const float *x, const float *gamma, float *dx_io, void *dx_bf16,
                       int rows, int D, void *stream);
+/* The same two on every row_step-th row of their [*, D] buffers (row i of the call is row i*row_step of x, y, dy and
+ * dx): the class-token rows (row_step = T) of the last block, see pcg_set_pooled_last_block. */
+int pcg_layernorm_fwd_rows(const float *x, const float *gamma, const float *beta, void *y_bf16, int rows, int D,
+                           int row_step, void *stream);
+int pcg_layernorm_bwd_rows(const void *dy_bf16, const float *x, const float *gamma, float *dx_io, void *dx_bf16,
+                           int rows, int D, int row_step, void *stream);
 
 /* ---- class token + positional embedding + ln_pre (ruclip/model.py:109-120) ------------------------------
  * patch_out f32 [n*g*g, D] -> v f32 [n*T, D] (pre-LN, stashed) and x0 f32 [n*T, D]. */
@@ -157,6 +163,14 @@ int pcg_attn_bwd(const void *qkv, const void *out, const void *d_out, const floa
 int pcg_attn_fwd_wide(const void *qkv, void *out, float *lse, int n, int T, int heads, void *stream);
 int pcg_attn_bwd_wide(const void *qkv, const void *out, const void *d_out, const float *lse, float *delta_ws,
                       void *d_qkv, int n, int T, int heads, void *stream);
+
+/* Class-token attention of the LAST block: query row 0 of every (cutout, head) against all T keys
+ * (ruclip/model.py:43-49 restricted to the one row that ruclip/model.py:126 reads).  head_stride = columns per head
+ * in qkv / out (pcg_head_stride).  fwd writes out[n*T + 0, :] and lse[n, :, 0] only; bwd writes ALL of d_qkv
+ * (dK, dV of every row, dQ of row 0, zeros in the other dQ rows) from d_out[n*T + 0, :]. */
+int pcg_attn_cls_fwd(const void *qkv, void *out, float *lse, int n, int T, int heads, int head_stride, void *stream);
+int pcg_attn_cls_bwd(const void *qkv, const void *out, const void *d_out, const float *lse, void *d_qkv, int n, int T,
+                     int heads, int head_stride, void *stream);
 
 /* ---- head: ln_post(CLS) @ proj -> L2 normalise -> spherical distance loss, forward AND gradient ---------
  * replaces ruclip/model.py:126-129 + F.normalize (models/open_clip.py:120-121) + CLIP.forward
@@ -216,6 +230,12 @@ int pcg_guidance_fwd(const pcg_guidance_args *a, void *stream);
 /* backward to the image: replaces autograd through everything above (dgrad only; weights are frozen,
  * perceptor/models/open_clip.py:73-76). */
 int pcg_guidance_bwd(const pcg_guidance_args *a, void *stream);
+/* The loss reads only the class-token row of the last block's output (ruclip/model.py:126), so by default
+ * pcg_guidance_fwd / _bwd run the last block's attention output, out-projection, ln_2 and MLP on the n class-token rows
+ * instead of all n*T rows (K and V projections, ln_1 and everything below stay full): the same loss and image gradient
+ * from 10/12 of one block's GEMM work less.  on = 0 restores the full last block (also: PCG_FULL_LAST_BLOCK=1 in the
+ * environment); returns the previous setting.  Takes effect for subsequent calls (captured CUDA graphs keep theirs). */
+int pcg_set_pooled_last_block(int on);
 /* number of kernels the last fwd / bwd call launched (for bench.py's gpu_launches). */
 int pcg_last_launch_count(void);
 

@@ -5,6 +5,7 @@
 // Replaces the eager op sequence of CLIP.forward (perceptor/losses/clip/clip.py:89-99) ->
 // OpenCLIP.encode_images (perceptor/models/open_clip.py:109-123) -> VisionTransformer.forward
 // (perceptor/models/ruclip/model.py:105-131) and the autograd tape behind it.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -187,6 +188,12 @@ int check_args(const pcg_guidance_args* a, bool bwd) {
     return 0;
 }
 
+// Last block on the class-token rows only (see pcg_set_pooled_last_block in pcg.h)
+bool g_pooled_last = []() {
+    const char* e = getenv("PCG_FULL_LAST_BLOCK");
+    return !(e != nullptr && e[0] == '1');
+}();
+
 #define PCG_TRY(expr)          \
     do {                       \
         int _rc = (expr);      \
@@ -203,6 +210,11 @@ extern "C" int pcg_abi_version(void) { return PCG_ABI_VERSION; }
 extern "C" int pcg_device_sm_count(void) { return sm_count(); }
 extern "C" int pcg_head_stride(int head_dim) { return head_dim == 64 ? 64 : 128; }
 extern "C" int pcg_last_launch_count(void) { return launch_count(); }
+extern "C" int pcg_set_pooled_last_block(int on) {
+    const int prev = g_pooled_last ? 1 : 0;
+    g_pooled_last = on != 0;
+    return prev;
+}
 
 extern "C" int pcg_profile_enable(int on) {
     g_prof_on = on != 0;
@@ -257,23 +269,39 @@ extern "C" int pcg_guidance_fwd(const pcg_guidance_args* a, void* stream) {
                           wk.patch_out, nullptr, D, stream));
     PCG_TRY(pcg_embed_fwd(wk.patch_out, w.cls, w.pos, w.ln_pre_g, w.ln_pre_b, st.v, stash_x(st, 0, keep), n, T, D,
                           stream));
+    const int hs = pcg_head_stride(c.head_dim);
     for (int l = 0; l < c.layers; ++l) {
         const pcg_layer_weights& lw = w.layers_host[l];
         const LayerStash ls = layer_stash(st, l, keep);
         float* x_in = stash_x(st, l, keep);
         float* x_out = stash_x(st, l + 1, keep);
+        // The head reads only the class-token row of the last block's output: there, K and V are projected for every
+        // row but q, the attention output, the out-projection, ln_2 and the MLP run on the n class-token rows
+        // (row stride T in the same buffers, so the backward finds everything where the full block would put it).
+        const bool pooled = g_pooled_last && l == c.layers - 1 && T > 1;
+        const int Mr = pooled ? n : M;          // rows of the row-wise ops after the K / V projection
+        const int rs = pooled ? T : 1;          // their row step
         PCG_TRY(pcg_layernorm_fwd(x_in, lw.ln1_g, lw.ln1_b, wk.y, M, D, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, 3 * Da, D, wk.y, D, lw.w_qkv, D, lw.b_qkv, nullptr, ls.qkv,
-                              nullptr, 3 * Da, stream));
-        PCG_TRY(wide ? pcg_attn_fwd_wide(ls.qkv, ls.o, ls.lse, n, T, c.heads, stream)
-                     : pcg_attn_fwd(ls.qkv, ls.o, ls.lse, n, T, c.heads, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_RESID_F32, c.act, M, D, Da, ls.o, Da, lw.w_out, Da, lw.b_out, x_in, ls.xb, nullptr,
-                              D, stream));
-        PCG_TRY(pcg_layernorm_fwd(ls.xb, lw.ln2_g, lw.ln2_b, wk.y, M, D, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BIAS_ACT, c.act, M, c.mlp, D, wk.y, D, lw.w_fc, D, lw.b_fc, nullptr, ls.h, wk.a,
-                              c.mlp, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_RESID_F32, c.act, M, D, c.mlp, wk.a, c.mlp, lw.w_proj, c.mlp, lw.b_proj, ls.xb,
-                              x_out, nullptr, D, stream));
+        if (!pooled) {
+            PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, 3 * Da, D, wk.y, D, lw.w_qkv, D, lw.b_qkv, nullptr, ls.qkv,
+                                  nullptr, 3 * Da, stream));
+            PCG_TRY(wide ? pcg_attn_fwd_wide(ls.qkv, ls.o, ls.lse, n, T, c.heads, stream)
+                         : pcg_attn_fwd(ls.qkv, ls.o, ls.lse, n, T, c.heads, stream));
+        } else {
+            const uint16_t* w_kv = static_cast<const uint16_t*>(lw.w_qkv) + static_cast<size_t>(Da) * D;
+            PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, 2 * Da, D, wk.y, D, w_kv, D, lw.b_qkv + Da, nullptr, ls.qkv + Da,
+                                  nullptr, 3 * Da, stream));
+            PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, n, Da, D, wk.y, T * D, lw.w_qkv, D, lw.b_qkv, nullptr, ls.qkv,
+                                  nullptr, T * 3 * Da, stream));
+            PCG_TRY(pcg_attn_cls_fwd(ls.qkv, ls.o, ls.lse, n, T, c.heads, hs, stream));
+        }
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_RESID_F32, c.act, Mr, D, Da, ls.o, rs * Da, lw.w_out, Da, lw.b_out, x_in, ls.xb,
+                              nullptr, rs * D, stream));
+        PCG_TRY(pcg_layernorm_fwd_rows(ls.xb, lw.ln2_g, lw.ln2_b, wk.y, Mr, D, rs, stream));
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BIAS_ACT, c.act, Mr, c.mlp, D, wk.y, rs * D, lw.w_fc, D, lw.b_fc, nullptr, ls.h, wk.a,
+                              rs * c.mlp, stream));
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_RESID_F32, c.act, Mr, D, c.mlp, wk.a, rs * c.mlp, lw.w_proj, c.mlp, lw.b_proj, ls.xb,
+                              x_out, nullptr, rs * D, stream));
     }
     PCG_TRY(pcg_head_loss(stash_x(st, c.layers, keep), w.ln_post_g, w.ln_post_b, w.proj, a->targets, a->tweights, n, T, D,
                           c.embed, a->targets ? a->n_targets : 0, a->loss_scale, a->normalize, a->loss_sum, a->enc_out,
@@ -297,20 +325,29 @@ extern "C" int pcg_guidance_bwd(const pcg_guidance_args* a, void* stream) {
     PCG_TRY(pcg_head_loss(stash_x(st, c.layers, true), w.ln_post_g, w.ln_post_b, w.proj, a->targets, a->tweights, n, T, D,
                           c.embed, a->targets ? a->n_targets : 0, a->d_enc ? 1.0f : a->loss_scale, a->normalize, nullptr,
                           nullptr, a->d_enc, nullptr, wk.dxb, wk.head_ws, stream));
+    const int hs = pcg_head_stride(c.head_dim);
     for (int l = c.layers - 1; l >= 0; --l) {
         const pcg_layer_weights& lw = w.layers_host[l];
         const LayerStash ls = layer_stash(st, l, true);
+        // last block: the gradient arrives on the class-token rows only (the head zeroes the others), and the forward
+        // kept only those rows of x_mid / act' / o -- the same row-stepped calls in reverse
+        const bool pooled = g_pooled_last && l == c.layers - 1 && T > 1;
+        const int Mr = pooled ? n : M;
+        const int rs = pooled ? T : 1;
         // MLP: dH = (dx W_proj) * act'(h) ; dy = dH W_fc ; dx += ln_2'(dy)
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_DACT, c.act, M, c.mlp, D, wk.dxb, D, lw.w_proj_t, D, nullptr, ls.h, wk.a, nullptr,
-                              c.mlp, stream));
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, c.mlp, wk.a, c.mlp, lw.w_fc_t, c.mlp, nullptr, nullptr, wk.y,
-                              nullptr, D, stream));
-        PCG_TRY(pcg_layernorm_bwd(wk.y, ls.xb, lw.ln2_g, nullptr, wk.dxb, M, D, stream));
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_DACT, c.act, Mr, c.mlp, D, wk.dxb, rs * D, lw.w_proj_t, D, nullptr, ls.h, wk.a,
+                              nullptr, rs * c.mlp, stream));
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, Mr, D, c.mlp, wk.a, rs * c.mlp, lw.w_fc_t, c.mlp, nullptr, nullptr, wk.y,
+                              nullptr, rs * D, stream));
+        PCG_TRY(pcg_layernorm_bwd_rows(wk.y, ls.xb, lw.ln2_g, nullptr, wk.dxb, Mr, D, rs, stream));
         // attention: dO = dx W_out ; dqkv = attn'(dO) ; dy = dqkv W_qkv ; dx += ln_1'(dy)
-        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, Da, D, wk.dxb, D, lw.w_out_t, D, nullptr, nullptr, wk.d_o, nullptr,
-                              Da, stream));
-        PCG_TRY(wide ? pcg_attn_bwd_wide(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream)
-                     : pcg_attn_bwd(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream));
+        PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, Mr, Da, D, wk.dxb, rs * D, lw.w_out_t, D, nullptr, nullptr, wk.d_o,
+                              nullptr, rs * Da, stream));
+        if (pooled)
+            PCG_TRY(pcg_attn_cls_bwd(ls.qkv, ls.o, wk.d_o, ls.lse, wk.dqkv, n, T, c.heads, hs, stream));
+        else
+            PCG_TRY(wide ? pcg_attn_bwd_wide(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream)
+                         : pcg_attn_bwd(ls.qkv, ls.o, wk.d_o, ls.lse, wk.delta, wk.dqkv, n, T, c.heads, stream));
         PCG_TRY(pcg_gemm_bf16(PCG_GEMM_BF16, c.act, M, D, 3 * Da, wk.dqkv, 3 * Da, lw.w_qkv_t, 3 * Da, nullptr, nullptr,
                               wk.y, nullptr, D, stream));
         PCG_TRY(pcg_layernorm_bwd(wk.y, stash_x(st, l, true), lw.ln1_g, nullptr, wk.dxb, M, D, stream));

@@ -59,12 +59,13 @@ template <int NV>
 __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, bf16* __restrict__ y,
-                                                                    int rows) {
+                                                                    int rows, int row_step) {
     grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     constexpr int D = NV * 128;
-    const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    if (blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5) >= rows) return;
+    // row_step > 1: every row_step-th row of x and y (the class-token rows of the last block)
+    const size_t row = static_cast<size_t>(blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5)) * row_step;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
     float4 v[NV];
 #pragma unroll
@@ -119,12 +120,12 @@ template <int NV, bool kF32>
 __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     float* __restrict__ dx_io, bf16* __restrict__ dx_bf16,
-                                                                    int rows) {
+                                                                    int rows, int row_step) {
     grid_dep_launch();  // a dependent (PDL) kernel may start its prologue while this grid drains
     constexpr int D = NV * 128;
-    const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    if (blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5) >= rows) return;
+    const size_t row = static_cast<size_t>(blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5)) * row_step;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
     float4* dxr = reinterpret_cast<float4*>(dx_io + static_cast<size_t>(row) * D);
@@ -466,31 +467,39 @@ static int check_d(const char* who, int D) {
     return 0;
 }
 
-extern "C" int pcg_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, int rows, int D,
-                                 void* stream) {
-    PCG_CHECK_ARG(x && gamma && beta && y_bf16 && rows > 0, "pcg_layernorm_fwd: bad arguments");
+extern "C" int pcg_layernorm_fwd_rows(const float* x, const float* gamma, const float* beta, void* y_bf16, int rows, int D,
+                                      int row_step, void* stream) {
+    PCG_CHECK_ARG(x && gamma && beta && y_bf16 && rows > 0 && row_step > 0, "pcg_layernorm_fwd: bad arguments");
     if (int rc = check_d("pcg_layernorm_fwd", D)) return rc;
     ProfileScope prof(PCG_PROF_LAYERNORM, 6.0 * rows * D, static_cast<cudaStream_t>(stream));
     PCG_DISPATCH_NV(D, layernorm_fwd_kernel, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream), x, gamma, beta,
-                    static_cast<bf16*>(y_bf16), rows);
+                    static_cast<bf16*>(y_bf16), rows, row_step);
     PCG_LAUNCH_CHECK("layernorm_fwd_kernel");
     return 0;
 }
+extern "C" int pcg_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, int rows, int D,
+                                 void* stream) {
+    return pcg_layernorm_fwd_rows(x, gamma, beta, y_bf16, rows, D, 1, stream);
+}
 
-extern "C" int pcg_layernorm_bwd(const void* dy_bf16, const float* x, const float* gamma, float* dx_io, void* dx_bf16,
-                                 int rows, int D, void* stream) {
-    PCG_CHECK_ARG(dy_bf16 && x && gamma && dx_bf16 && rows > 0, "pcg_layernorm_bwd: bad arguments");
+extern "C" int pcg_layernorm_bwd_rows(const void* dy_bf16, const float* x, const float* gamma, float* dx_io, void* dx_bf16,
+                                      int rows, int D, int row_step, void* stream) {
+    PCG_CHECK_ARG(dy_bf16 && x && gamma && dx_bf16 && rows > 0 && row_step > 0, "pcg_layernorm_bwd: bad arguments");
     if (int rc = check_d("pcg_layernorm_bwd", D)) return rc;
     ProfileScope prof(PCG_PROF_LAYERNORM, (dx_io ? 16.0 : 10.0) * rows * D, static_cast<cudaStream_t>(stream));
     if (dx_io != nullptr) {
         PCG_DISPATCH_NV2(D, layernorm_bwd_kernel, true, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream),
-                         static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows);
+                         static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows, row_step);
     } else {
         PCG_DISPATCH_NV2(D, layernorm_bwd_kernel, false, ceil_div(rows, kRowsPerBlock), static_cast<cudaStream_t>(stream),
-                         static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows);
+                         static_cast<const bf16*>(dy_bf16), x, gamma, dx_io, static_cast<bf16*>(dx_bf16), rows, row_step);
     }
     PCG_LAUNCH_CHECK("layernorm_bwd_kernel");
     return 0;
+}
+extern "C" int pcg_layernorm_bwd(const void* dy_bf16, const float* x, const float* gamma, float* dx_io, void* dx_bf16,
+                                 int rows, int D, void* stream) {
+    return pcg_layernorm_bwd_rows(dy_bf16, x, gamma, dx_io, dx_bf16, rows, D, 1, stream);
 }
 
 extern "C" int pcg_embed_fwd(const float* patch_out, const float* cls, const float* pos, const float* gamma,

@@ -16,7 +16,7 @@ LIB_PATH = PKG_DIR / "libpcg.so"
 ACT_QUICKGELU, ACT_GELU = 0, 1
 GEMM_BF16, GEMM_BIAS_ACT, GEMM_RESID_F32, GEMM_DACT, GEMM_F32 = 0, 1, 2, 3, 4
 CUT_STRIDE = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -85,6 +85,11 @@ SIGNATURES = {
     "pcg_gemm_bf16": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "pcg_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "pcg_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "pcg_layernorm_fwd_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pcg_layernorm_bwd_rows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pcg_attn_cls_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pcg_attn_cls_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pcg_set_pooled_last_block": (_i, [_i]),
     "pcg_embed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pcg_head_stride": (_i, [_i]),

@@ -103,6 +103,40 @@ def attn_bwd_wide(qkv, out, d_out, lse, n, tokens, heads):
     return d_qkv
 
 
+def attn_cls_fwd(qkv, n, tokens, heads, head_stride=64):
+    """Class-token row only (last block): returns (out [n*T, heads*hs] with row n*T+0 written, lse [n, heads, T])."""
+    out = torch.zeros((n * tokens, heads * head_stride), dtype=bf16, device=qkv.device)
+    lse = torch.zeros((n, heads, tokens), dtype=torch.float32, device=qkv.device)
+    native.check(native.lib().pcg_attn_cls_fwd(_p(qkv), _p(out), _p(lse), n, tokens, heads, head_stride,
+                                               native.stream_ptr()), "pcg_attn_cls_fwd")
+    return out, lse
+
+
+def attn_cls_bwd(qkv, out, d_out, lse, n, tokens, heads, head_stride=64):
+    d_qkv = torch.full_like(qkv, float("nan"))  # the kernel must write every element
+    native.check(native.lib().pcg_attn_cls_bwd(_p(qkv), _p(out), _p(d_out), _p(lse), _p(d_qkv), n, tokens, heads,
+                                               head_stride, native.stream_ptr()), "pcg_attn_cls_bwd")
+    return d_qkv
+
+
+def layernorm_fwd_rows(x, gamma, beta, y, rows, row_step):
+    """LayerNorm of rows 0, row_step, 2*row_step, ... of x into the same rows of y (bf16, in place)."""
+    native.check(native.lib().pcg_layernorm_fwd_rows(_p(x), _p(gamma), _p(beta), _p(y), rows, x.shape[1], row_step,
+                                                     native.stream_ptr()), "pcg_layernorm_fwd_rows")
+    return y
+
+
+def layernorm_bwd_rows(dy, x, gamma, dx_bf16, rows, row_step):
+    native.check(native.lib().pcg_layernorm_bwd_rows(_p(dy), _p(x), _p(gamma), None, _p(dx_bf16), rows, x.shape[1],
+                                                     row_step, native.stream_ptr()), "pcg_layernorm_bwd_rows")
+    return dx_bf16
+
+
+def set_pooled_last_block(on: bool) -> bool:
+    """Last transformer block on the class-token rows only (default) or in full; returns the previous setting."""
+    return bool(native.lib().pcg_set_pooled_last_block(int(bool(on))))
+
+
 def head_loss(x, ln_g, ln_b, proj, targets, tweights, n, tokens, scale=1.0, normalize=True, want_grad=True,
               d_enc=None):
     d, e = proj.shape

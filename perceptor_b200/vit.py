@@ -60,14 +60,27 @@ class VitShape:
     def kpad(self) -> int:
         return (self.kpatch + 63) // 64 * 64
 
-    def flops_per_cutout(self) -> float:
-        """Algorithmic forward+backward FLOPs per cutout (dgrad-only backward; SURVEY.md §8d / BASELINE.md §4)."""
+    def flops_per_cutout(self, pooled_last_block: bool = False) -> float:
+        """Algorithmic forward+backward FLOPs per cutout (dgrad-only backward; SURVEY.md §8d / BASELINE.md §4).
+
+        pooled_last_block=False counts what the reference's dense computation does (every token through every block).
+        True counts what the default sequencer executes: in the last block only the K / V projections (and their
+        dgrad GEMM) see all T tokens; q, the attention row, the out-projection and the MLP run on the class token.
+        """
         g2, d, t, l = self.grid**2, self.width, self.tokens, self.layers
         patch = 2 * g2 * self.kpatch * d
-        linear = l * t * (8 * d * d + 4 * d * self.mlp)  # QKV 6D^2 + out 2D^2 + MLP 2 * 2 * D * mlp per token
-        attn = l * 4 * t * t * d
+        per_token = 8 * d * d + 4 * d * self.mlp  # QKV 6D^2 + out 2D^2 + MLP 2 * 2 * D * mlp per token
         head = 2 * d * self.embed
-        return (patch + linear + attn + head) + (patch + linear + 2 * attn + head)
+        full = l if not pooled_last_block else l - 1
+        linear_f = linear_b = full * t * per_token
+        attn_f, attn_b = full * 4 * t * t * d, full * 8 * t * t * d
+        if pooled_last_block:
+            one = 2 * d * d + 2 * d * d + 4 * d * self.mlp          # q, out-projection, MLP of the class-token row
+            linear_f += t * 4 * d * d + one                          # K and V of every token
+            linear_b += t * 6 * d * d + (2 * d * d + 4 * d * self.mlp)  # full dqkv dgrad GEMM; dout, dfc, dproj on one row
+            attn_f += 4 * t * d
+            attn_b += 8 * t * d
+        return (patch + linear_f + attn_f + head) + (patch + linear_b + attn_b + head)
 
 
 SHAPES = {

@@ -69,6 +69,32 @@ def test_tiny_config_matches_oracle(cuda_device):
     assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
 
 
+@pytest.mark.parametrize("shape_name,n_rows", [("tiny", 4), ("ViT-B-32", 5), ("ViT-L-14", 3)])
+def test_pooled_last_block_equals_the_full_last_block(cuda_device, shape_name, n_rows):
+    """The default sequencer runs the last block's attention output, out-projection, ln_2 and MLP on the class-token
+    rows only (the loss reads nothing else, ruclip/model.py:126).  The full last block (pcg_set_pooled_last_block(0))
+    must give the same loss and image gradient up to bf16 rounding of different tile shapes -- and it, too, must match
+    the oracle."""
+    from perceptor_b200 import ops
+    shape = TINY if shape_name == "tiny" else SHAPES[shape_name]
+    g = torch.Generator().manual_seed(5)
+    hw = 64 if shape_name == "tiny" else 256
+    images = torch.rand(2, 3, hw, hw, generator=g)
+    rows = sampler_oracle.sample_cutouts(torch.Generator().manual_seed(3), 2, hw, hw, n_rows, 1.0, hw // 2, hw)[1::2][:n_rows]
+    prev = ops.set_pooled_last_block(True)
+    try:
+        loss_p, loss_ref, grad_p, grad_ref, _ = run_case(cuda_device, shape, images, rows)
+        ops.set_pooled_last_block(False)
+        loss_f, _, grad_f, _, _ = run_case(cuda_device, shape, images, rows)
+    finally:
+        ops.set_pooled_last_block(prev)
+    assert abs(loss_p - loss_f) <= 2e-3 * abs(loss_f), (loss_p, loss_f)
+    assert cosine(grad_p, grad_f) >= 0.9995, cosine(grad_p, grad_f)
+    for loss, grad in ((loss_p, grad_p), (loss_f, grad_f)):
+        assert abs(loss - loss_ref) <= LOSS_RTOL * abs(loss_ref), (loss, loss_ref)
+        assert cosine(grad, grad_ref) >= GRAD_COS, cosine(grad, grad_ref)
+
+
 def test_vit_b32_config1_matches_oracle(cuda_device):
     """BASELINE.json configs[0]: ViT-B/32, one 3x256x256 image, 16 cutouts."""
     shape = SHAPES["ViT-B-32"]

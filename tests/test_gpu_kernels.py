@@ -131,6 +131,31 @@ def test_layernorm(cuda_device, rows, d):
     check_close(acc, dx0.to(bf16).float() + xr.grad, 4e-3, "layernorm bwd (bf16 accumulate in place)")
 
 
+@pytest.mark.parametrize("rows,step,d", [(5, 50, 768), (128, 257, 1024), (3, 7, 1280)])
+def test_layernorm_row_step(cuda_device, rows, step, d):
+    """pcg_layernorm_fwd_rows / _bwd_rows: every step-th row (the class-token rows of the last block) and nothing else."""
+    g = torch.Generator(device="cpu").manual_seed(rows + step)
+    total = rows * step
+    x = (torch.randn(total, d, generator=g) * 2 - 0.3).to(cuda_device)
+    gamma = (torch.rand(d, generator=g) + 0.5).to(cuda_device)
+    beta = torch.randn(d, generator=g).to(cuda_device)
+    y = torch.full((total, d), 7.0, dtype=bf16, device=cuda_device)
+    ops.layernorm_fwd_rows(x, gamma, beta, y, rows, step)
+    want = torch.nn.functional.layer_norm(x[::step], (d,), gamma, beta, 1e-5)
+    check_close(y[::step], want, 4e-3, "layernorm fwd rows")
+    mask = torch.ones(total, dtype=torch.bool, device=cuda_device)
+    mask[::step] = False
+    assert bool((y[mask] == 7.0).all()), "rows between the steps were touched"
+    dy = torch.randn(total, d, generator=g).to(cuda_device, bf16)
+    acc0 = torch.randn(total, d, generator=g).to(cuda_device, bf16)
+    xr = x[::step].clone().requires_grad_()
+    torch.nn.functional.layer_norm(xr, (d,), gamma, beta, 1e-5).backward(dy[::step].float())
+    acc = acc0.clone()
+    ops.layernorm_bwd_rows(dy, x, gamma, acc, rows, step)
+    check_close(acc[::step], acc0[::step].float() + xr.grad, 4e-3, "layernorm bwd rows")
+    assert bool((acc[mask] == acc0[mask]).all()), "rows between the steps were touched"
+
+
 # ------------------------------------------------------------------------------------------------ embed
 @pytest.mark.parametrize("n,grid,d", [(3, 7, 768), (2, 16, 1024), (5, 4, 128)])
 def test_embed(cuda_device, n, grid, d):
@@ -247,6 +272,45 @@ def test_attention_wide_heads(cuda_device, n, t, heads, hd):
         assert float(d_qkv[..., hd:].abs().max()) == 0.0
     for i, (name, ref) in enumerate((("dq", qr.grad), ("dk", kr.grad), ("dv", vr.grad))):
         check_close(d_qkv[:, :, i, :, :hd], ref, 1.5e-2, f"wide attention {name} hd={hd}")
+
+
+@pytest.mark.parametrize("n,t,heads,hd", [(3, 257, 16, 64), (2, 50, 12, 64), (1, 577, 4, 64), (5, 197, 3, 64), (1, 2, 1, 64),
+                                          (2, 257, 4, 80), (1, 50, 2, 88), (130, 17, 2, 64)])
+def test_attention_class_token_row(cuda_device, n, t, heads, hd):
+    """pcg_attn_cls_fwd / _bwd (the last block: one query row per head against all keys) against fp32 torch attention
+    restricted to row 0; head dim 80 / 88 in the padded 128-column layout.  The backward must write all of d_qkv:
+    dK / dV of every row, dQ of row 0 and exact zeros in the other dQ rows (the wrapper pre-fills NaN)."""
+    hs = 64 if hd == 64 else 128
+    g = torch.Generator(device="cpu").manual_seed(n + t + heads + hd)
+    q, k, v = (torch.randn(n, t, heads, hd, generator=g) for _ in range(3))
+    q = q * hd**-0.5 * 2.0
+    d_o = torch.zeros(n, t, heads, hd)
+    d_o[:, 0] = torch.randn(n, heads, hd, generator=g)  # the gradient arrives on the class-token row only
+
+    def padded(x):
+        out = torch.zeros(n, t, heads, hs)
+        out[..., :hd] = x
+        return out.reshape(n * t, heads * hs)
+
+    qkv = torch.cat([padded(q), padded(k), padded(v)], dim=1).to(cuda_device, bf16)
+    out, lse = ops.attn_cls_fwd(qkv, n, t, heads, hs)
+    qr, kr, vr = (x.to(cuda_device, bf16).float().requires_grad_() for x in (q, k, v))
+    s = torch.einsum("nqhd,nkhd->nhqk", qr, kr)
+    o_ref = torch.einsum("nhqk,nkhd->nqhd", torch.softmax(s, dim=-1), vr)
+    out4 = out.float().reshape(n, t, heads, hs)
+    check_close(out4[:, 0, :, :hd], o_ref[:, 0], 6e-3, f"class-token attention fwd hd={hd}")
+    assert float(out4[:, 1:].abs().max()) == 0.0 if t > 1 else True  # only row 0 is written
+    check_close(lse[:, :, 0], torch.logsumexp(s, dim=-1)[:, :, 0], 1e-3, "class-token lse")
+    o_ref.backward(d_o.to(cuda_device, bf16).float())
+    # the product path feeds the bf16 class-token row the forward kernel wrote
+    d_qkv = ops.attn_cls_bwd(qkv, out, padded(d_o).to(cuda_device, bf16), lse, n, t, heads, hs)
+    assert torch.isfinite(d_qkv.float()).all(), "class-token attention bwd left elements unwritten"
+    d5 = d_qkv.float().reshape(n, t, 3, heads, hs)
+    if hd < hs:
+        assert float(d5[..., hd:].abs().max()) == 0.0
+    assert float(d5[:, 1:, 0].abs().max()) == 0.0 if t > 1 else True
+    for i, (name, ref) in enumerate((("dq", qr.grad), ("dk", kr.grad), ("dv", vr.grad))):
+        check_close(d5[:, :, i, :, :hd], ref, 1.0e-2, f"class-token attention {name} hd={hd}")
 
 
 def test_attention_random_shapes_repeated(cuda_device):
