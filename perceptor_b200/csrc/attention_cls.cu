@@ -77,11 +77,14 @@ attn_cls_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
     const bf16* base = qkv + static_cast<size_t>(n) * T * ld + static_cast<size_t>(h) * HS + sub * 8;
     float qf[8];
     unpack8(*reinterpret_cast<const uint4*>(base), qf);
-    for (int j = kslot; j < T; j += KSTEP) {
+    // the trip count is warp-uniform (the group sums shuffle across the whole warp): rows past T are predicated off
+    for (int j0 = warp * KPW; j0 < T; j0 += KSTEP) {
+        const int j = j0 + lane / LPR;
+        const bool ok = j < T;
         float kf[8];
-        unpack8(*reinterpret_cast<const uint4*>(base + j * ld + Da), kf);
+        unpack8(ok ? *reinterpret_cast<const uint4*>(base + j * ld + Da) : make_uint4(0u, 0u, 0u, 0u), kf);
         const float s = group_sum<LPR>(dot8(qf, kf));
-        if (sub == 0) sc[j] = s;
+        if (ok && sub == 0) sc[j] = s;
     }
     __syncthreads();
     float mx = -INFINITY;
@@ -140,7 +143,7 @@ attn_cls_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, 
     __shared__ float red[kClsWarps][HS];
     const int h = blockIdx.x, n = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane % LPR, kslot = warp * KPW + lane / LPR;
+    const int sub = lane % LPR;
     const size_t Da = static_cast<size_t>(heads) * HS, ld = 3 * Da;
     const size_t row0 = static_cast<size_t>(n) * T;
     const size_t col = static_cast<size_t>(h) * HS + sub * 8;
@@ -153,12 +156,15 @@ attn_cls_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, 
     const float delta = group_sum<LPR>(dot8(dof, of));
     const float L = lse[(static_cast<size_t>(n) * heads + h) * T];
     float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j = kslot; j < T; j += KSTEP) {
+    for (int j0 = warp * KPW; j0 < T; j0 += KSTEP) {  // warp-uniform trip count: the group sums shuffle across the warp
+        const int j = j0 + lane / LPR;
+        const bool ok = j < T;
         float kf[8], vf[8];
-        unpack8(*reinterpret_cast<const uint4*>(base + j * ld + Da), kf);
-        unpack8(*reinterpret_cast<const uint4*>(base + j * ld + 2 * Da), vf);
+        unpack8(ok ? *reinterpret_cast<const uint4*>(base + j * ld + Da) : make_uint4(0u, 0u, 0u, 0u), kf);
+        unpack8(ok ? *reinterpret_cast<const uint4*>(base + j * ld + 2 * Da) : make_uint4(0u, 0u, 0u, 0u), vf);
         const float s = group_sum<LPR>(dot8(qf, kf));
         const float dp = group_sum<LPR>(dot8(dof, vf));
+        if (!ok) continue;
         const float p = __expf(s - L);
         const float ds = p * (dp - delta);
         *reinterpret_cast<uint4*>(dbase + j * ld + 2 * Da) =

@@ -166,7 +166,7 @@ def test_exact_gelu_towers_match_oracle(cuda_device):
     eng_q = GuidanceEngine(TINY, sd, cuda_device, native.ACT_QUICKGELU)
     loss_q = GuidanceLossFn.apply(images.to(cuda_device), eng_q, eng_q.plan_cutouts(np.asarray(rows, dtype=np.int32)),
                                   targets.to(cuda_device), tw.to(cuda_device), 1.0, None)
-    assert abs(float(loss_q) - float(loss.detach())) > 1e-4 * abs(float(loss.detach()))
+    assert abs(float(loss_q) - float(loss.detach())) > 2e-5 * abs(float(loss.detach()))
     assert losses.OpenCLIP("ViT-L-14", "laion2b_s32b_b82k").model.act == native.ACT_GELU
     assert losses.OpenCLIP("ViT-L-14", "openai").model.act == native.ACT_QUICKGELU
 
