@@ -289,6 +289,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int n0 = (tile % num_n) * BN;
             const int row_base = m0 + quarter * 32;
             const int col_base = n0 + half * kHalfN + sub_col * 4;  // this lane's first column of chunk 0
+            // Bias: requested one 32-column chunk ahead (chunk 0 before the wait for the accumulator).  A load issued in
+            // the chunk that uses it sits exposed -- an L2 round trip, four times per tile -- on the chain that has to stay
+            // shorter than the next tile's main loop.  DACT (a dgrad epilogue) never has a bias.
+            constexpr bool kMayBias = MODE != PCG_GEMM_DACT;
+            auto load_bias = [&](int c) {
+                const int col = col_base + c * 32;
+                return (kMayBias && p.bias != nullptr && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col))
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            float4 bias_cur = load_bias(0);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * kHalfN;
@@ -305,8 +315,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (c + 1 < kChunks) tmem_ld_32x32(taddr0 + (c + 1) * 32, r);  // in flight while chunk c is written out
                 __syncwarp();
                 const bool col_ok = col < p.N;
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                const float4 bias4 = bias_cur;
+                if (c + 1 < kChunks) bias_cur = load_bias(c + 1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int lrow = i * 4 + sub_row;

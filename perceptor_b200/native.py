@@ -10,8 +10,11 @@ from pathlib import Path
 
 import torch
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libpcg.so"
+# PCG_LIBRARY: development aid for A/B runs of kernel variants (tools/build_variant.py); the product is the in-tree file
+LIB_PATH = Path(os.environ["PCG_LIBRARY"]) if os.environ.get("PCG_LIBRARY") else PKG_DIR / "libpcg.so"
 
 ACT_QUICKGELU, ACT_GELU = 0, 1
 GEMM_BF16, GEMM_BIAS_ACT, GEMM_RESID_F32, GEMM_DACT, GEMM_F32 = 0, 1, 2, 3, 4
