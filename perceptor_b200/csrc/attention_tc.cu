@@ -945,6 +945,359 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd2P
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// forward, persistent, every score row split over two warps (production for 130 <= T <= 257: two key tiles)
+// ---------------------------------------------------------------------------------------------------------
+// The persistent kernel above walks one item in ~11 000 clk with FOUR softmax warps: thread = row, 256 scores per
+// thread in sequence (row max 1400 clk, exponentials 4800, output 1900), so a (cutout, head, tile) item is a chain of
+// dependent phases and the SM's MUFU and tensor pipes sit at a third of their rate even with two CTAs resident.  Here
+// the same item is worked on by EIGHT softmax warps: warps 0-3 own the keys < 128 of their 32 rows (S columns [0, 128),
+// P into [0, 64)), warps 4-7 the keys >= 128 (S columns [128, 256), P into [128, 192)); the two threads of a row
+// exchange their partial row max (and the edge key's score) and later their partial sums through shared memory with a
+// 64-thread named barrier per lane quarter, and each takes 32 of the 64 output columns.  Every phase of the chain is
+// half as long, and four warps per scheduler instead of two keep the MUFU pipe fed.  Tensor memory, the operand
+// ring, the MMA / TMA thread and the edge warp are those of attn_fwd_persist_kernel.
+constexpr int kFwd3Threads = 320;  // warps 0-3 keys < 128, 4-7 keys >= 128, 8 TMA + MMA, 9 edge query row
+constexpr int kFwd3OffEx = kFwd2OffX + 2 * 768 + 1024;  // float ex_mx[2][128], ex_sx[128], ex_sum[2][128]
+constexpr int kFwd3OffBar = kFwd3OffEx + 5 * 512;
+constexpr int kFwd3SmemBytes = kFwd3OffBar + 16 * 8 + 64 + 1024;
+
+struct Fwd3Params : Fwd2Params {
+    uint32_t heads_magic, grid_magic;  // ceil(2^32 / heads), ceil(2^32 / gridDim.x): exact quotients for the sizes the host admits
+};
+
+__device__ __forceinline__ float exp32_f2(const uint32_t (&v)[32], float mb, uint32_t tdst, float sum) {
+    uint32_t pk[16];
+    float2 s01 = make_float2(0.f, 0.f);
+    const float2 l2 = make_float2(kLog2e, kLog2e), nmb = make_float2(-mb, -mb);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 a = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), l2, nmb);
+        const float2 e = make_float2(exp2f(a.x), exp2f(a.y));
+        s01 = __fadd2_rn(s01, e);
+        pk[j] = pack_bf16(e.x, e.y);
+    }
+    tmem_st<16>(tdst, pk);
+    return sum + (s01.x + s01.y);
+}
+
+__global__ void __launch_bounds__(kFwd3Threads, 2)
+attn_fwd_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd3Params p) {
+    grid_dep_launch();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sm_k = sm;
+    uint8_t* sm_v = sm + kFwdOffV;
+    uint8_t* sm_q0 = sm + kFwd2OffQ;
+    float* xvec = reinterpret_cast<float*>(sm + kFwd2OffX);  // slot s: k_x = xvec + 192 s, v_x = + 64, q_x = + 128
+    float* pbuf = xvec + 384;
+    float* ex_mx = reinterpret_cast<float*>(sm + kFwd3OffEx);  // [2][128]
+    float* ex_sx = ex_mx + 256;                                // [128]
+    float* ex_sum = ex_sx + 128;                               // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kFwd3OffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = p.heads * kHd, nv = p.nv, nk = p.nk;
+    const int nblk = (nk + 127) >> 7;  // 2 here
+    const int G = gridDim.x;
+    // Item it of this CTA is w = it * G + (blockIdx.x + it) % G: round `it` of the grid is rotated by `it`, so that with
+    // an even grid a CTA alternates between the two query tiles of a head.  Only the second tile carries the edge
+    // query row, the one part of an item that a single warp works through on the CUDA cores (~9000 clk): with
+    // w = blockIdx.x + it * G every odd CTA had it on every item and set the kernel's time.
+    const int full_rounds = p.items / G;
+    const int n_my = full_rounds + (((static_cast<int>(blockIdx.x) + full_rounds) % G) < p.items - full_rounds * G ? 1 : 0);
+    // (no integer division here: the emulation's MUFU.RCP queues behind the exponentials of sixteen softmax warps, and
+    // this sits between two items of every warp; the host passes ceil(2^32 / d) for both divisors)
+    auto decode = [&](int it, int& n, int& h, int& q0) {
+        const uint32_t x = blockIdx.x + static_cast<uint32_t>(it);
+        const int w = it * G + static_cast<int>(x - __umulhi(x, p.grid_magic) * static_cast<uint32_t>(G));
+        const int nh = w >> 1;  // two query tiles per (cutout, head)
+        q0 = (w & 1) * 128;
+        n = static_cast<int>(__umulhi(static_cast<uint32_t>(nh), p.heads_magic));
+        h = nh - n * p.heads;
+    };
+    auto load_qk = [&](int it) {
+        int n, h, q0;
+        decode(it, n, h, q0);
+        uint64_t* bar = &bars[kB2FullQK + (it & 1)];
+        mbar_arrive_expect_tx(bar, (nblk + 1) * kBlkBytes);
+        tma_load_3d(&map_qkv, bar, sm_q0 + (it & 1) * kBlkBytes, h * kHd, q0, n, kEvictFirst);
+        for (int i = 0; i < nblk; ++i)
+            tma_load_3d(&map_qkv, bar, sm_k + i * kBlkBytes, D + h * kHd, i * 128, n, kEvictNormal);
+    };
+    auto load_v = [&](int it) {
+        int n, h, q0;
+        decode(it, n, h, q0);
+        mbar_arrive_expect_tx(&bars[kB2FullV], nblk * kBlkBytes);
+        for (int i = 0; i < nblk; ++i)
+            tma_load_3d(&map_qkv, &bars[kB2FullV], sm_v + i * kBlkBytes, 2 * D + h * kHd, i * 128, n, kEvictNormal);
+    };
+    auto load_x = [&](int it, uint32_t& xq, uint32_t& xk, uint32_t& xv) {
+        int n, h, q0;
+        decode(it, n, h, q0);
+        const bf16* xrow_g = p.qkv + (static_cast<size_t>(n) * p.T + nv) * 3 * D + h * kHd + 2 * lane;
+        xq = *reinterpret_cast<const uint32_t*>(xrow_g);
+        xk = *reinterpret_cast<const uint32_t*>(xrow_g + D);
+        xv = *reinterpret_cast<const uint32_t*>(xrow_g + 2 * D);
+    };
+
+    uint32_t xq = 0, xk = 0, xv = 0;
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(&bars[kB2FullQK], 1);
+            mbar_init(&bars[kB2FullQK + 1], 1);
+            mbar_init(&bars[kB2FullV], 1);
+            mbar_init(&bars[kB2SReady], 1);
+            mbar_init(&bars[kB2PHi], 4);
+            mbar_init(&bars[kB2PLo], 4);
+            mbar_init(&bars[kB2OReady], 1);
+            mbar_init(&bars[kB2TmemFree], 8);
+            mbar_init(&bars[kB2Done], 8);
+            mbar_init(&bars[kB2Done + 1], 8);
+            mbar_init(&bars[kB2XReady], 1);
+            mbar_init(&bars[kB2XReady + 1], 1);
+            mbar_init(&bars[kB2EdgeK], 1);
+            mbar_init(&bars[kB2EdgeV], 1);
+            fence_barrier_init();
+            load_qk(0);
+            load_v(0);
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    } else if (warp == 9) {
+        load_x(0, xq, xk, xv);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const size_t cta_id = blockIdx.x;
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[cta_id * 32 + 30] = clock64(), p.trace[cta_id * 32 + 29] = n_my;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+            const int ksteps = nk >> 4;
+#pragma unroll 1
+            for (int it = 0; it < n_my; ++it) {
+                const int s = it & 1;
+                const bool tr = (it == kTraceItem) && p.trace != nullptr;
+                // ---- S(it) = Q K^T, as soon as the operands are in and O(it - 1) has left tensor memory
+                mbar_wait_c(&bars[kB2FullQK + s], (it >> 1) & 1);
+                if (tr) p.trace[cta_id * 32 + 10] = clock64();
+                if (it > 0) mbar_wait_c(&bars[kB2TmemFree], (it - 1) & 1);
+                if (tr) p.trace[cta_id * 32 + 11] = clock64();
+                tc_fence_after();
+                mma_tile_x_rows(tmem, sm_q0 + s * kBlkBytes, sm_k, nk);
+                umma_commit(&bars[kB2SReady]);
+                if (it + 1 < n_my) {
+                    if (it >= 1) mbar_wait_c(&bars[kB2Done + (s ^ 1)], ((it - 1) >> 1) & 1);
+                    mbar_wait_c(&bars[kB2SReady], it & 1);
+                    mbar_wait_c(&bars[kB2EdgeK], it & 1);
+                    load_qk(it + 1);
+                }
+                if (tr) p.trace[cta_id * 32 + 12] = clock64();
+                // ---- O(it) = P V with A = P from tensor memory, keys >= 128 first
+                mbar_wait_c(&bars[kB2FullV], it & 1);
+                mbar_wait_c(&bars[kB2PHi], it & 1);
+                if (tr) p.trace[cta_id * 32 + 13] = clock64();
+                tc_fence_after();
+                for (int ks = 8; ks < ksteps; ++ks)
+                    umma_f16_ts(tmem + kFwdColO, tmem + kFwdColPHi + (ks - 8) * 8,
+                                umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)), idesc_pv, ks != 8);
+                mbar_wait_c(&bars[kB2PLo], it & 1);
+                if (tr) p.trace[cta_id * 32 + 14] = clock64();
+                tc_fence_after();
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_f16_ts(tmem + kFwdColO, tmem + ks * 8, umma_smem_desc_sw128(smem_u32(sm_v + ks * 2048)),
+                                idesc_pv, 1);
+                umma_commit(&bars[kB2OReady]);
+                if (it + 1 < n_my) {
+                    mbar_wait_c(&bars[kB2OReady], it & 1);
+                    if (tr) p.trace[cta_id * 32 + 15] = clock64();
+                    mbar_wait_c(&bars[kB2EdgeV], it & 1);
+                    load_v(it + 1);
+                    if (tr) p.trace[cta_id * 32 + 16] = clock64();
+                }
+            }
+        }
+    } else if (warp < 8) {
+        const int grp = warp >> 2, quarter = warp & 3;  // grp 0: keys < 128, grp 1: keys >= 128
+        const int r = quarter * 32 + lane;              // query row in the tile == TMEM lane
+        const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int nch = (nk + 31) >> 5;                       // 32-column chunks of S (5..8)
+        const int my_ch = grp == 0 ? 4 : nch - 4;             // chunks of this group
+        const uint32_t s_col = grp == 0 ? 0u : 128u;          // first S column of this group
+        const uint32_t p_col = grp == 0 ? 0u : kFwdColPHi;    // first packed P column of this group
+        float sx_next = 0.f;
+        bool have_sx = false;
+#pragma unroll 1
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it & 1;
+            int n, h, q0;
+            decode(it, n, h, q0);
+            const float* kx = xvec + 192 * s;
+            const float* vx = kx + 64;
+            const bool tr = (it == kTraceItem) && quarter == 0 && p.trace != nullptr && lane == 0;
+            const int tb = grp == 0 ? 0 : 17 - 4;  // group 1 stamps S ready / exp done / epilogue done at 17 / 18 / 19
+            if (it == kTraceItem + 1 && warp == 0 && p.trace != nullptr && lane == 0) p.trace[cta_id * 32 + 9] = clock64();
+            if (tr && grp == 0) p.trace[cta_id * 32 + 0] = clock64(), p.trace[cta_id * 32 + 28] = 1 + (q0 + 128 >= nv);
+            // score against the edge key (group 0; normally taken one item ahead, below)
+            float sx = sx_next;
+            if (grp == 0 && !have_sx) {
+                mbar_wait_c(&bars[kB2XReady + s], (it >> 1) & 1);
+                mbar_wait_c(&bars[kB2FullQK + s], (it >> 1) & 1);
+                sx = row_dot(sm_q0 + s * kBlkBytes, r, kx);
+            }
+            have_sx = false;
+            mbar_wait_c(&bars[kB2SReady], it & 1);
+            tc_fence_after();
+            if (tr) p.trace[cta_id * 32 + tb + 4] = clock64();
+            uint32_t va[32];
+            float mx = grp == 0 ? sx : -INFINITY;
+#pragma unroll 1
+            for (int i = 0; i < my_ch; ++i) {
+                tmem_ld<32>(trow + s_col + 32 * i, va);
+                tmem_wait_ld();
+                mask_cols32(va, static_cast<int>(s_col) + 32 * i, nv);
+                mx = max32(va, mx);
+            }
+            // the row's other half
+            ex_mx[grp * 128 + r] = mx;
+            if (grp == 0) ex_sx[r] = sx;
+            named_bar_sync(1 + quarter, 64);
+            mx = fmaxf(mx, ex_mx[(grp ^ 1) * 128 + r]);
+            sx = ex_sx[r];
+            if (tr && grp == 0) p.trace[cta_id * 32 + 5] = clock64();
+            const float mb = mx * kLog2e;
+            float sum = 0.f;
+#pragma unroll 1
+            for (int i = 0; i < my_ch; ++i) {
+                tmem_ld<32>(trow + s_col + 32 * i, va);
+                tmem_wait_ld();
+                mask_cols32(va, static_cast<int>(s_col) + 32 * i, nv);
+                sum = exp32_f2(va, mb, trow + p_col + 16 * i, sum);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[grp == 0 ? kB2PLo : kB2PHi]);
+            if (tr) p.trace[cta_id * 32 + (grp == 0 ? 6 : 18)] = clock64();
+            const float px = exp2f(fmaf(sx, kLog2e, -mb));
+            ex_sum[grp * 128 + r] = sum;
+            named_bar_sync(1 + quarter, 64);
+            sum += ex_sum[(grp ^ 1) * 128 + r] + px;
+            if (grp == 0 && q0 + r < nv) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + q0 + r] = mx + logf(sum);
+            const float inv = 1.0f / sum;
+            // the tensor pipe needs ~1500 clk for O: group 0 takes the next item's edge score now if its Q tile and
+            // edge vectors have landed (both barriers stay complete until this warp's item it + 1)
+            if (grp == 0 && it + 1 < n_my && mbar_test_wait(&bars[kB2XReady + (s ^ 1)], ((it + 1) >> 1) & 1) &&
+                mbar_test_wait(&bars[kB2FullQK + (s ^ 1)], ((it + 1) >> 1) & 1)) {
+                sx_next = row_dot(sm_q0 + (s ^ 1) * kBlkBytes, r, xvec + 192 * (s ^ 1));
+                have_sx = true;
+            }
+            mbar_wait_c(&bars[kB2OReady], it & 1);
+            tc_fence_after();
+            if (tr && grp == 0) p.trace[cta_id * 32 + 7] = clock64();
+            tmem_ld<32>(trow + kFwdColO + 32 * grp, va);
+            tmem_wait_ld();
+            // this thread's half of O is in registers: tensor memory may take S of the next item
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2TmemFree]);
+            bf16* grow = p.out + (static_cast<size_t>(n) * p.T + q0 + r) * D + h * kHd + 32 * grp;
+            const bool row_ok = q0 + r < nv;
+            const float* vxg = vx + 32 * grp;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4 xa = *reinterpret_cast<const float4*>(vxg + g * 8);
+                const float4 xb = *reinterpret_cast<const float4*>(vxg + g * 8 + 4);
+                const uint4 o = make_uint4(pack_bf16(fmaf(px, xa.x, __uint_as_float(va[8 * g])) * inv,
+                                                     fmaf(px, xa.y, __uint_as_float(va[8 * g + 1])) * inv),
+                                           pack_bf16(fmaf(px, xa.z, __uint_as_float(va[8 * g + 2])) * inv,
+                                                     fmaf(px, xa.w, __uint_as_float(va[8 * g + 3])) * inv),
+                                           pack_bf16(fmaf(px, xb.x, __uint_as_float(va[8 * g + 4])) * inv,
+                                                     fmaf(px, xb.y, __uint_as_float(va[8 * g + 5])) * inv),
+                                           pack_bf16(fmaf(px, xb.z, __uint_as_float(va[8 * g + 6])) * inv,
+                                                     fmaf(px, xb.w, __uint_as_float(va[8 * g + 7])) * inv));
+                if (row_ok) *reinterpret_cast<uint4*>(grow + g * 8) = o;
+            }
+            // this item's Q slot and edge vectors (v_x above was their last reader in this warp) may be refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2Done + s]);
+            if (tr) p.trace[cta_id * 32 + (grp == 0 ? 8 : 19)] = clock64();
+        }
+    } else {
+        // edge warp: as in attn_fwd_persist_kernel
+#pragma unroll 1
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it & 1;
+            int n, h, q0;
+            decode(it, n, h, q0);
+            const bool has_edge_row = (q0 + 128 >= nv);
+            float* kx = xvec + 192 * s;
+            float* vx = kx + 64;
+            float* qx = kx + 128;
+            if (it >= 2) mbar_wait_c(&bars[kB2Done + s], ((it - 2) >> 1) & 1);
+            qx[2 * lane] = bf_lo(xq), qx[2 * lane + 1] = bf_hi(xq);
+            kx[2 * lane] = bf_lo(xk), kx[2 * lane + 1] = bf_hi(xk);
+            vx[2 * lane] = bf_lo(xv), vx[2 * lane + 1] = bf_hi(xv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2XReady + s]);
+            const float sxx = warp_sum(fmaf(bf_lo(xq), bf_lo(xk), bf_hi(xq) * bf_hi(xk)));  // q_x . k_x
+            if (it + 1 < n_my) load_x(it + 1, xq, xk, xv);
+            const bool tr = (it == kTraceItem) && p.trace != nullptr && lane == 0;
+            if (tr) p.trace[cta_id * 32 + 20] = clock64();
+            mbar_wait_c(&bars[kB2FullQK + s], (it >> 1) & 1);
+            if (tr) p.trace[cta_id * 32 + 21] = clock64();
+            float sc[8];
+            if (has_edge_row) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = lane + 32 * jj;
+                    sc[jj] = (j < nv) ? row_dot(sm_k, j, qx) : -INFINITY;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2EdgeK]);
+            if (tr) p.trace[cta_id * 32 + 22] = clock64();
+            if (has_edge_row) {
+                float mx = sxx;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) mx = fmaxf(mx, sc[jj]);
+                mx = warp_max(mx);
+                const float mb = mx * kLog2e;
+                float part = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    sc[jj] = exp2f(fmaf(sc[jj], kLog2e, -mb));
+                    part += sc[jj];
+                    pbuf[lane + 32 * jj] = sc[jj];
+                }
+                const float exx = exp2f(fmaf(sxx, kLog2e, -mb));
+                const float sum = warp_sum(part) + exx;
+                __syncwarp();
+                mbar_wait_c(&bars[kB2FullV], it & 1);
+                edge_gemv(pbuf, sm_v, nv, exx, vx, p.out + (static_cast<size_t>(n) * p.T + nv) * D + h * kHd, 1.0f / sum,
+                          lane);
+                if (lane == 0) p.lse[(static_cast<size_t>(n) * p.heads + h) * p.T + nv] = mx + logf(sum);
+            } else {
+                mbar_wait_c(&bars[kB2FullV], it & 1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[kB2EdgeV]);
+            if (tr) p.trace[cta_id * 32 + 23] = clock64();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[cta_id * 32 + 31] = clock64();
+    if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // forward, long sequences (T - 1 > 256: ViT-L/14 @336 has 576 + 1 tokens)
 // ---------------------------------------------------------------------------------------------------------
 // Same CTA shape as above (cutout, head, 128-query tile; 2 CTAs / SM), but S no longer fits tensor memory, so the
@@ -2760,6 +3113,12 @@ bool g_fwd_persist = []() {
     return !(e != nullptr && e[0] == '0');
 }();
 
+// PCG_ATTN_SPLIT=0 keeps the four-softmax-warp persistent forward for T - 1 > 128 too (A/B)
+bool g_fwd_split = []() {
+    const char* e = getenv("PCG_ATTN_SPLIT");
+    return !(e != nullptr && e[0] == '0');
+}();
+
 bool g_bwd_persist = []() {
     const char* e = getenv("PCG_ATTN_PERSIST");
     return !(e != nullptr && e[0] == '0');
@@ -2785,6 +3144,11 @@ extern "C" int pcg_attn_set_legacy(int on) {  // test hook: force the mma.sync k
 extern "C" int pcg_attn_set_persist(int mode) {
     g_fwd_persist = mode == 1 || mode == 3;
     g_bwd_persist = mode == 1 || mode == 2;
+    return 0;
+}
+
+extern "C" int pcg_attn_set_split(int on) {  // test / benchmark hook: 0 = four softmax warps per forward CTA, 1 = eight
+    g_fwd_split = on != 0;
     return 0;
 }
 
@@ -2823,6 +3187,21 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
         return 0;
     }
     const int nv = T - 1;
+    // two key tiles: every score row split over two warps.  (The size limits keep the kernel's multiply-high quotients exact.)
+    if (g_fwd_persist && g_fwd_split && nv > 128 && heads >= 2 && heads <= 1024 && static_cast<long long>(n) * heads * 2 < (1ll << 22)) {
+        static PerDeviceOnce split_configured;
+        PCG_ONCE_PER_DEVICE(split_configured, PCG_CUDA(cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3SmemBytes)));
+        const int items = n * heads * 2;
+        const int grid = std::min(items, 2 * sm_count());
+        Fwd3Params p3;
+        static_cast<Fwd2Params&>(p3) = Fwd2Params{T, heads, nv, (nv + 15) & ~15, 2, items, static_cast<const bf16*>(qkv),
+                                                  static_cast<bf16*>(out), lse, g_trace, 0};
+        p3.heads_magic = static_cast<uint32_t>(((1ull << 32) + heads - 1) / heads);
+        p3.grid_magic = static_cast<uint32_t>(((1ull << 32) + grid - 1) / grid);
+        attn_fwd_split_kernel<<<grid, kFwd3Threads, kFwd3SmemBytes, s>>>(map, p3);
+        PCG_LAUNCH_CHECK("attn_fwd_split_kernel");
+        return 0;
+    }
     if (g_fwd_persist) {
         static PerDeviceOnce persist_configured;
         PCG_ONCE_PER_DEVICE(persist_configured, PCG_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2SmemBytes)));

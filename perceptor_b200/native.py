@@ -123,7 +123,7 @@ def profile_collect() -> dict:
     return {k: {"ms": ms[i], "work": work[i], "count": cnt[i]} for i, k in enumerate(PROF_KINDS)}
 # test hook, not part of the public header
 _EXTRA = {"pcg_gemm_bf16_bn": (_i, [_i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
-          "pcg_gemm_set_variant": (_i, [_i]), "pcg_attn_set_legacy": (_i, [_i]), "pcg_attn_set_persist": (_i, [_i]), "pcg_attn_set_trace": (_i, [_vp]), "pcg_sampler_set_scalar": (_i, [_i])}
+          "pcg_gemm_set_variant": (_i, [_i]), "pcg_attn_set_legacy": (_i, [_i]), "pcg_attn_set_persist": (_i, [_i]), "pcg_attn_set_split": (_i, [_i]), "pcg_attn_set_trace": (_i, [_vp]), "pcg_sampler_set_scalar": (_i, [_i])}
 
 _lib = None
 

@@ -218,6 +218,17 @@ def test_attention_persistent_ctas(cuda_device, n, t, heads, persist):
         native.lib().pcg_attn_set_persist(1)
 
 
+@pytest.mark.parametrize("n,t,heads", [(40, 257, 16), (33, 197, 12), (150, 130, 2), (3, 257, 16), (2, 192, 3), (5, 257, 3)])
+def test_attention_forward_four_softmax_warps(cuda_device, n, t, heads):
+    """T - 1 > 128 defaults to the forward whose score rows are split over two warps (attn_fwd_split_kernel);
+    pcg_attn_set_split(0) keeps the four-softmax-warp persistent forward, which must stay correct (A/B baseline)."""
+    native.lib().pcg_attn_set_split(0)
+    try:
+        run_attention_case(cuda_device, n, t, heads, 1)
+    finally:
+        native.lib().pcg_attn_set_split(1)
+
+
 def run_attention_case(cuda_device, n, t, heads, tc):
     """tc=1 routes T >= 66 through the tcgen05 kernels (the default; T > 257 streams the keys with an online
     softmax: 258 / 385 leave one key in the last chunk, 400 fifteen, 1025 fills eight chunks; T <= 64 with an even

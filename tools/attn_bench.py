@@ -16,8 +16,10 @@ def main():
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent fwd+bwd, 2: persistent bwd only, 3: persistent fwd only")
+    ap.add_argument("--split", type=int, default=1, help="0: four softmax warps per forward CTA, 1: eight (rows split over two warps)")
     args = ap.parse_args()
     native.lib().pcg_attn_set_persist(args.persist)
+    native.lib().pcg_attn_set_split(args.split)
     dev = torch.device("cuda", 0)
     n, t, h = args.n, args.t, args.heads
     d = h * 64
@@ -43,7 +45,7 @@ def main():
         tb += e[1].elapsed_time(e[2])
     tf, tb = tf / args.iters, tb / args.iters
     fl = 4.0 * t * t * 64 * h * n
-    print(f"persist={args.persist} n={n} T={t} heads={h}: fwd {tf * 1e3:.1f} us ({fl / tf / 1e9:.0f} TF/s)  bwd {tb * 1e3:.1f} us ({2 * fl / tb / 1e9:.0f} TF/s algorithmic)")
+    print(f"persist={args.persist} split={args.split} n={n} T={t} heads={h}: fwd {tf * 1e3:.1f} us ({fl / tf / 1e9:.0f} TF/s)  bwd {tb * 1e3:.1f} us ({2 * fl / tb / 1e9:.0f} TF/s algorithmic)")
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@ from perceptor_b200 import native, ops  # noqa: E402
 
 # persistent forward: stamps of each CTA's SECOND item (steady state), warp 0
 FWD2 = {0: "item start", 9: "next item start", 4: "S ready", 5: "max pass done", 6: "exp pass done", 7: "O ready", 8: "epilogue done",
+        17: "grp1: S ready", 18: "grp1: exp pass done", 19: "grp1: epilogue done",
         10: "ctl: Q+K landed", 11: "ctl: tmem free (S issue)", 12: "ctl: next Q+K requested", 13: "ctl: PV hi issued",
         14: "ctl: P lo seen", 15: "ctl: O retired", 16: "ctl: next V requested", 20: "edge: vectors written",
         21: "edge: K landed", 22: "edge: K dots done", 23: "edge: row done"}
@@ -31,10 +32,14 @@ BWD = {0: "start", 1: "first loads landed", 2: "edge vectors ready", 3: "edge ge
        17: "ctl b1 P/dS seen", 18: "ctl b2 P/dS seen", 19: "ctl b3 P/dS seen", 20: "delta done", 21: "ctl issued first S/dP"}
 
 
-def show(trace, names, title):
+def show(trace, names, title, flag=None):
     t = trace.cpu().double()
     valid = t[:, 0] > 0
+    if flag is not None:
+        valid &= t[:, 28] == flag
     t = t[valid]
+    if t.shape[0] == 0:
+        return
     rel = t - t[:, :1]
     print(f"--- {title}: {t.shape[0]} CTAs, cycles since CTA start (median / p90)")
     order = sorted(names, key=lambda k: float(rel[:, k][t[:, k] > 0].median()) if (t[:, k] > 0).any() else 1e18)
@@ -53,8 +58,11 @@ def main():
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--persist", type=int, default=1, help="0: one tile per CTA (round-1 kernels), 1: persistent fwd+bwd, 2: persistent bwd only, 3: persistent fwd only")
+    ap.add_argument("--split", type=int, default=1)
+    ap.add_argument("--no-bwd", action="store_true")
     args = ap.parse_args()
     native.lib().pcg_attn_set_persist(args.persist)
+    native.lib().pcg_attn_set_split(args.split)
     dev = torch.device("cuda", 0)
     n, t, h = args.n, args.t, args.heads
     d = h * 64
@@ -91,8 +99,15 @@ def main():
         life = tt[:, 31] - tt[:, 30]
         print(f"persistent forward: {tt.shape[0]} CTAs, items per CTA {tt[:, 29].min():.0f}-{tt[:, 29].max():.0f}, CTA lifetime "
               f"median {life.median():.0f} max {life.max():.0f} clk, per item {float((life / tt[:, 29]).median()):.0f} clk")
-    show(trace, FWD2 if args.persist in (1, 3) else FWD,
-         "forward (persistent, one steady-state item of each CTA)" if args.persist in (1, 3) else "forward")
+    if args.persist in (1, 3) and args.split and t >= 130:
+        show(trace, FWD2, "forward (split rows), traced item WITHOUT the edge query row", flag=1)
+        show(trace, FWD2, "forward (split rows), traced item WITH the edge query row", flag=2)
+    else:
+        show(trace, FWD2 if args.persist in (1, 3) else FWD,
+             "forward (persistent, one steady-state item of each CTA)" if args.persist in (1, 3) else "forward")
+    if args.no_bwd:
+        native.lib().pcg_attn_set_trace(None)
+        return
     trace.zero_()
     ops.attn_bwd(qkv, out, d_out, lse, n, t, h)
     torch.cuda.synchronize()
