@@ -1,13 +1,14 @@
 #!/bin/bash
 # A/B of libpcg.so variants on ONE box (boxes of the pool differ by +-3 %): tools/ab.sh ROUNDS name=path [name=path ...]
-# ("intree" = perceptor_b200/libpcg.so).  Each run: bench.py headline workload, 10 steps, no side legs; prints
+# ("intree" = perceptor_b200/libpcg.so; append ,VAR=val to set environment variables for that variant).  Each run: bench.py headline workload, 10 steps, no side legs; prints
 # cutouts/s, ms/step and the per-family ms of the profiled pass.
 rounds=$1; shift
 for r in $(seq 1 $rounds); do
   for v in "$@"; do
-    name=${v%%=*}; path=${v#*=}
+    name=${v%%=*}; rest=${v#*=}; path=${rest%%,*}; envs=""
+    [ "$rest" != "$path" ] && envs=$(echo "${rest#*,}" | tr "," " ")   # name=path,VAR=val,VAR2=val2
     if [ "$path" = "intree" ]; then unset PCG_LIBRARY; else export PCG_LIBRARY=$path; fi
-    timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu --no-parity --no-other-configs --no-full-last-block ${AB_ARGS} > /tmp/ab.json 2>/tmp/ab.err \
+    env $envs timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu --no-parity --no-other-configs --no-full-last-block ${AB_ARGS} > /tmp/ab.json 2>/tmp/ab.err \
       && python - "$name" <<'PY'
 import json, sys
 d = json.load(open("/tmp/ab.json"))
