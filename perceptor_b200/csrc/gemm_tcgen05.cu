@@ -108,12 +108,20 @@ __device__ __forceinline__ float2 act_and_grad2(float2 h, float2& grad) {
     }
 }
 
-template <int BN, int MODE, int ACT, int CTAS>
+// MC (CTA pairs only): clusters of FOUR CTAs = two pairs that work on the same 256 output rows and on adjacent column
+// tiles (n, n + 1).  Both pairs need the same A rows, so every CTA fetches 64 of its pair-half's 128 rows and
+// multicasts them to the CTA of the same rank in the other pair: a k-block costs an SM 8 KB of A + 16 KB of B from L2
+// instead of 16 + 16.  (The GEMMs of the step sit at the L2's practical throughput: their rates follow
+// operand + epilogue bytes per tile, see DESIGN.md.)  A stage may be refilled once BOTH pairs' MMAs have read it: the
+// empty barriers collect one tcgen05.commit from each pair leader.
+template <int BN, int MODE, int ACT, int CTAS, bool MC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p) {
+    static_assert(!MC || CTAS == 2, "multicast clusters are built from CTA pairs");
     using Cfg = TileCfg<BN, CTAS>;
-    constexpr int kTileM = BM * CTAS;  // rows of one output tile (per cluster)
+    constexpr int kCluster = CTAS * (MC ? 2 : 1);
+    constexpr int kTileM = BM * CTAS;  // rows of one output tile (per pair / CTA)
     constexpr int kStages = Cfg::kStages;
     constexpr int kBBytes = Cfg::kBBytes;
 
@@ -136,12 +144,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int num_m = (p.M + kTileM - 1) / kTileM;
     const int num_n = (p.N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + BK - 1) / BK;
     // a CTA pair walks the same tiles; rank 1 owns rows [128, 256) of the tile and B rows [BN/2, BN)
-    const int cta_rank = (CTAS == 2) ? static_cast<int>(cluster_ctarank()) : 0;
-    const int tile0 = static_cast<int>(blockIdx.x) / CTAS;
-    const int tile_step = static_cast<int>(gridDim.x) / CTAS;
+    const int crank = (CTAS == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int cta_rank = crank & 1;
+    const int pair = MC ? (crank >> 1) : 0;
+    // work units of a cluster: output tiles, or (MC) a row tile x two adjacent column tiles, one per pair
+    const int units_n = MC ? (num_n >> 1) : num_n;
+    const int num_tiles = num_m * units_n;
+    const int tile0 = static_cast<int>(blockIdx.x) / kCluster;
+    const int tile_step = static_cast<int>(gridDim.x) / kCluster;
+    auto tile_m = [&](int t) { return t / units_n; };
+    auto tile_n = [&](int t) { return MC ? 2 * (t % units_n) + pair : t % units_n; };
 
     if (warp == kWarpTma && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -150,7 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == kWarpMma && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], MC ? 2 : 1);  // MC: one commit from each pair of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -182,11 +196,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-                const int m0 = (tile / num_n) * kTileM + cta_rank * BM;
-                const int n0 = (tile % num_n) * BN + cta_rank * (BN / CTAS);
+                const int m0 = tile_m(tile) * kTileM + cta_rank * BM;
+                const int n0 = tile_n(tile) * BN + cta_rank * (BN / CTAS);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if constexpr (CTAS == 2) {
+                    if constexpr (MC) {
+                        // rows [64 pair, 64 pair + 64) of this CTA's 128 A rows, to this CTA and to its twin in the other pair
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));
+                        tma_load_2d_2sm_mc(&map_a, &full_bar[stage], smem_a + stage * kABytes + pair * (kABytes / 2), kb * BK,
+                                           m0 + pair * (BM / 2), static_cast<uint16_t>(0x5u << cta_rank), kHintA);
+                        tma_load_2d_2sm(&map_b, &full_bar[stage], smem_b + stage * kBBytes, kb * BK, n0, kEvictLast);
+                    } else if constexpr (CTAS == 2) {
                         // both CTAs' bytes land on the even CTA's barrier, which alone expects them
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));
                         tma_load_2d_2sm(&map_a, &full_bar[stage], smem_a + stage * kABytes, kb * BK, m0, kHintA);
@@ -230,8 +250,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             umma_f16(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
                     }
                     if constexpr (CTAS == 2) {
-                        umma_commit_2sm(&empty_bar[stage]);  // frees the slot in both CTAs when these MMAs retire
-                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[as]);
+                        // frees the slot in both CTAs (MC: in all four) when these MMAs retire
+                        umma_commit_2sm_mask(&empty_bar[stage], MC ? 0xF : 0x3);
+                        if (kb == num_kb - 1) umma_commit_2sm_mask(&tfull_bar[as], static_cast<uint16_t>(0x3u << (2 * pair)));
                     } else {
                         umma_commit(&empty_bar[stage]);
                         if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
@@ -267,8 +288,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         auto prefetch_aux = [&](int t, int c, uint32_t(&dst)[8][kAuxWords]) {
             if constexpr (kHasAux) {
                 const int tt = min(t, num_tiles - 1);
-                const int rb = (tt / num_n) * kTileM + cta_rank * BM + quarter * 32 + sub_row;
-                const int col = min((tt % num_n) * BN + half * kHalfN + c * 32 + sub_col * 4, p.N - 4);
+                const int rb = tile_m(tt) * kTileM + cta_rank * BM + quarter * 32 + sub_row;
+                const int col = min(tile_n(tt) * BN + half * kHalfN + c * 32 + sub_col * 4, p.N - 4);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const size_t off = static_cast<size_t>(min(rb + i * 4, p.M - 1)) * p.ldo + col;
@@ -288,8 +309,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * kTileM + cta_rank * BM;
-            const int n0 = (tile % num_n) * BN;
+            const int m0 = tile_m(tile) * kTileM + cta_rank * BM;
+            const int n0 = tile_n(tile) * BN;
             const int row_base = m0 + quarter * 32;
             const int col_base = n0 + half * kHalfN + sub_col * 4;  // this lane's first column of chunk 0
             // Bias: requested one 32-column chunk ahead (chunk 0 before the wait for the accumulator).  A load issued in
@@ -454,14 +475,46 @@ bool g_pdl_enabled = []() {
     return e != nullptr && e[0] == '1';
 }();
 
-template <int BN, int MODE, int ACT, int CTAS>
+// clusters of four that the device keeps resident at once (GPCs with 18 SMs hold four of them and leave a TPC idle)
+template <typename Kernel>
+int max_clusters_of_4(Kernel kernel, int smem, int* out) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    PCG_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+    *out = n;
+    return 0;
+}
+
+template <int BN, int MODE, int ACT, int CTAS, bool MC = false>
 int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
     using Cfg = TileCfg<BN, CTAS>;
+    constexpr int kCluster = CTAS * (MC ? 2 : 1);
     static PerDeviceOnce configured;
-    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)));
-    const int tiles = ceil_div(p.M, BM * CTAS) * ceil_div(p.N, BN);
-    const int slots = sm_count() / CTAS;  // clusters (or CTAs) that run concurrently
-    const int grid = (tiles < slots ? tiles : slots) * CTAS;
+    PCG_ONCE_PER_DEVICE(configured, PCG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, ACT, CTAS, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)));
+    const int tiles = ceil_div(p.M, BM * CTAS) * (MC ? ceil_div(p.N, BN) / 2 : ceil_div(p.N, BN));
+    int slots = sm_count() / kCluster;  // clusters (or CTAs) that run concurrently
+    if constexpr (MC) {
+        static int resident[64] = {0};
+        int dev = 0;
+        PCG_CUDA(cudaGetDevice(&dev));
+        if (dev < 64 && resident[dev] == 0) {
+            int n = 0;
+            if (int rc = max_clusters_of_4(gemm_tcgen05_kernel<BN, MODE, ACT, CTAS, MC>, Cfg::kSmem, &n)) return rc;
+            resident[dev] = n > 0 ? n : 1;
+        }
+        if (dev < 64) slots = resident[dev] < slots ? resident[dev] : slots;
+    }
+    const int grid = (tiles < slots ? tiles : slots) * kCluster;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -471,7 +524,7 @@ int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     int n_attr = 0;
     if constexpr (CTAS == 2) {
         attr[n_attr].id = cudaLaunchAttributeClusterDimension;
-        attr[n_attr].val.clusterDim.x = 2;
+        attr[n_attr].val.clusterDim.x = kCluster;
         attr[n_attr].val.clusterDim.y = 1;
         attr[n_attr].val.clusterDim.z = 1;
         ++n_attr;
@@ -483,26 +536,26 @@ int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     }
     cfg.attrs = attr;
     cfg.numAttrs = n_attr;
-    PCG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, ACT, CTAS>, ma, mb, p));
+    PCG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, ACT, CTAS, MC>, ma, mb, p));
     PCG_LAUNCH_CHECK("gemm_tcgen05_kernel");
     return 0;
 }
-template <int BN, int MODE, int CTAS>
+template <int BN, int MODE, int CTAS, bool MC = false>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
     if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
-        if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU, CTAS>(ma, mb, p, stream);
+        if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU, CTAS, MC>(ma, mb, p, stream);
     }
-    return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU, CTAS>(ma, mb, p, stream);
+    return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU, CTAS, MC>(ma, mb, p, stream);
 }
 
-template <int BN, int CTAS = 1>
+template <int BN, int CTAS = 1, bool MC = false>
 int dispatch_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
     switch (mode) {
-        case PCG_GEMM_BF16: return launch_gemm<BN, PCG_GEMM_BF16, CTAS>(ma, mb, p, s);
-        case PCG_GEMM_BIAS_ACT: return launch_gemm<BN, PCG_GEMM_BIAS_ACT, CTAS>(ma, mb, p, s);
-        case PCG_GEMM_RESID_F32: return launch_gemm<BN, PCG_GEMM_RESID_F32, CTAS>(ma, mb, p, s);
-        case PCG_GEMM_DACT: return launch_gemm<BN, PCG_GEMM_DACT, CTAS>(ma, mb, p, s);
-        case PCG_GEMM_F32: return launch_gemm<BN, PCG_GEMM_F32, CTAS>(ma, mb, p, s);
+        case PCG_GEMM_BF16: return launch_gemm<BN, PCG_GEMM_BF16, CTAS, MC>(ma, mb, p, s);
+        case PCG_GEMM_BIAS_ACT: return launch_gemm<BN, PCG_GEMM_BIAS_ACT, CTAS, MC>(ma, mb, p, s);
+        case PCG_GEMM_RESID_F32: return launch_gemm<BN, PCG_GEMM_RESID_F32, CTAS, MC>(ma, mb, p, s);
+        case PCG_GEMM_DACT: return launch_gemm<BN, PCG_GEMM_DACT, CTAS, MC>(ma, mb, p, s);
+        case PCG_GEMM_F32: return launch_gemm<BN, PCG_GEMM_F32, CTAS, MC>(ma, mb, p, s);
         default: return set_error(-1, "pcg_gemm_bf16: unknown mode %d", mode);
     }
 }
@@ -539,6 +592,12 @@ float pair_cost(int M, int N) {
     return static_cast<float>(waves) * 256.0f * 0.92f;
 }
 
+// multicast clusters of two pairs (see the kernel): PCG_GEMM_MC=0 / 1, pcg_gemm_set_variant(2) forces them on
+bool g_mc_enabled = []() {
+    const char* e = getenv("PCG_GEMM_MC");
+    return e != nullptr && e[0] == '1';
+}();
+
 bool g_pair_enabled = []() {
     const char* e = getenv("PCG_GEMM_PAIR");
     return !(e != nullptr && e[0] == '0');
@@ -561,17 +620,20 @@ int gemm_bf16_impl(int mode, int act, int M, int N, int K, const void* A, int ld
     // them, any other force_bn the single-CTA kernel
     float single_cost = 0.f;
     const int single_bn = choose_bn(M, N, &single_cost);
-    const bool pair = force_bn ? force_bn == 512
+    const bool pair = force_bn ? (force_bn == 512 || force_bn == 1024)
                                : (g_pair_enabled && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= sm_count() / 2 &&
                                   pair_cost(M, N) <= single_cost);
     const int bn = pair ? 256 : (force_bn ? force_bn : single_bn);
+    // two pairs per cluster sharing A: needs an even number of column tiles and at least two row tiles of work per pair
+    const bool mc = pair && (g_mc_enabled || force_bn == 1024) && N % 512 == 0;
     CUtensorMap ma, mb;
-    int rc = get_tensor_map(&ma, A, M, K, lda, BM);
+    int rc = get_tensor_map(&ma, A, M, K, lda, mc ? BM / 2 : BM);
     if (rc) return rc;
     rc = get_tensor_map(&mb, B, N, K, ldb, pair ? 128 : bn);
     if (rc) return rc;
     GemmParams p{M, N, K, bias, aux, out, out2, ldo, act};
     ProfileScope prof(PCG_PROF_GEMM, 2.0 * M * N * K, stream);
+    if (mc) return dispatch_mode<256, 2, true>(mode, ma, mb, p, stream);
     if (pair) return dispatch_mode<256, 2>(mode, ma, mb, p, stream);
     switch (bn) {
         case 256: return dispatch_mode<256>(mode, ma, mb, p, stream);
@@ -589,8 +651,10 @@ extern "C" int pcg_gemm_bf16(int mode, int act, int M, int N, int K, const void*
     return pcg::gemm_bf16_impl(mode, act, M, N, K, A, lda, B, ldb, bias, aux, out, out2, ldo, 0,
                                static_cast<cudaStream_t>(stream));
 }
-extern "C" int pcg_gemm_set_variant(int v) {  // tools / tests: 0 = single-CTA kernels only, 1 = CTA pairs allowed
+// tools / tests: 0 = single-CTA kernels only, 1 = CTA pairs allowed, 2 = CTA pairs in multicast clusters of four
+extern "C" int pcg_gemm_set_variant(int v) {
     pcg::g_pair_enabled = v != 0;
+    pcg::g_mc_enabled = v == 2;
     return 0;
 }
 // test hook: force the N tile width (64/128/192/256)

@@ -321,6 +321,28 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
         : "memory");
 }
 
+// The same load multicast to the CTAs in `cta_mask` (cluster ranks): the box lands at the same offset of every
+// destination CTA's shared memory and its bytes are counted on the mbarrier at `bar`'s offset in the even CTA of each
+// destination's pair.
+__device__ __forceinline__ void tma_load_2d_2sm_mc(const void* desc, uint64_t* bar, void* smem_dst, int32_t crd_inner,
+                                                   int32_t crd_outer, uint16_t cta_mask, uint64_t cache_hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPeerBitMask),
+          "r"(crd_inner), "r"(crd_outer), "h"(cta_mask), "l"(cache_hint)
+        : "memory");
+}
+// tcgen05.commit of a pair with an explicit multicast mask (cluster ranks whose copy of `bar` receives the arrival)
+__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // cp.async / ldmatrix / mma.sync (used by the short-sequence attention kernels)
 // ----------------------------------------------------------------------------------------------

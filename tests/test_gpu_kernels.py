@@ -47,7 +47,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
-@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256, 512])  # 512 = CTA pair (cta_group::2, 256 x 256 tiles)
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256, 512, 1024])  # 512 = CTA pair (cta_group::2, 256 x 256 tiles), 1024 = two pairs per cluster, A multicast
 def test_gemm_plain(cuda_device, m, n, k, bn):
     g = torch.Generator(device="cpu").manual_seed(m * 7 + n * 3 + k)
     a = torch.randn(m, k, generator=g).to(cuda_device, bf16)
@@ -62,7 +62,7 @@ def test_gemm_plain(cuda_device, m, n, k, bn):
 
 @pytest.mark.parametrize("m,n,k", [(300, 3072, 768), (257, 1024, 1024), (4112, 4096, 1024)])
 @pytest.mark.parametrize("act", [native.ACT_QUICKGELU, native.ACT_GELU])
-@pytest.mark.parametrize("bn", [256, 512])
+@pytest.mark.parametrize("bn", [256, 512, 1024])
 def test_gemm_epilogues(cuda_device, m, n, k, act, bn):
     g = torch.Generator(device="cpu").manual_seed(11 + m)
     a = torch.randn(m, k, generator=g).to(cuda_device, bf16)
