@@ -97,6 +97,23 @@ class GuidanceEngine:
     def _method_for_size(self, s: int) -> int:
         return LANCZOS3 if s >= self.shape.image_size else CUBIC
 
+    def _table_ids_for_sizes(self, sizes: np.ndarray) -> np.ndarray:
+        """Resize-table id of every (square) cutout size: a lookup array filled on first use (the per-call dictionary this
+        replaces cost 0.2 ms of host time per step, which an end-to-end step that reads its loss back cannot hide)."""
+        lut = getattr(self, "_size_lut", None)
+        top = int(sizes.max()) + 1
+        if lut is None or lut.size < top:
+            grown = np.full(max(top, 1024), -1, dtype=np.int32)
+            if lut is not None:
+                grown[:lut.size] = lut
+            self._size_lut = lut = grown
+        tid = lut[sizes]
+        if (tid < 0).any():
+            for s in np.unique(sizes[tid < 0]):
+                lut[int(s)] = self.tables.table_id(int(s), self._method_for_size(int(s)))
+            tid = lut[sizes]
+        return tid
+
     def plan_cutouts(self, rows: np.ndarray, rank: int = 0, world: int = 1, b_offset: int | None = None) -> CutPlan:
         """rows: [N,4] square cutouts (b,y0,x0,size) or [N,5] boxes (b,y0,x0,h,w) of ALL ranks; this rank takes the
         contiguous shard `cutouts.shard_rows(N, rank, world)`.  `b_offset` (not None: image-sharded mode) re-bases the
@@ -111,8 +128,7 @@ class GuidanceEngine:
             dev[:, :3] = local[:, :3]
             if rows.shape[1] == 4:
                 sizes = local[:, 3]
-                ids = {int(s): self.tables.table_id(int(s), self._method_for_size(int(s))) for s in np.unique(sizes)}
-                tid = np.vectorize(ids.__getitem__, otypes=[np.int32])(sizes)
+                tid = self._table_ids_for_sizes(sizes)
                 dev[:, 3] = dev[:, 4] = sizes
                 dev[:, 5] = dev[:, 6] = tid
             else:

@@ -38,6 +38,9 @@ class _TextImageLoss(torch.nn.Module):
         self.max_size = max_size
         self.process_group = process_group
         self.generator = generator if generator is not None else torch.Generator().manual_seed(int(seed))
+        # the module's own generator may be drawn from one call ahead (see _plan_ahead); a caller's generator never is
+        self._own_generator = generator is None
+        self._ahead = None
         self.encodings = None
         self.weights = None
         self.last_cutouts: np.ndarray | None = None
@@ -107,10 +110,39 @@ class _TextImageLoss(torch.nn.Module):
             self.last_cutouts = rows
             plan = eng.plan_cutouts(rows, rank, world, b_offset=rank * b_local)
             return GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, False)
-        rows = self._cutout_rows(images)
+        key = (tuple(images.shape), rank or 0, world or 1, id(eng), torch.cuda.current_stream(eng.device).cuda_stream)
+        rows, plan = self._take_ahead(key)
+        if rows is None:
+            rows = self._cutout_rows(images)
+            plan = eng.plan_cutouts(rows, rank or 0, world or 1)
         self.last_cutouts = rows
-        plan = eng.plan_cutouts(rows, rank or 0, world or 1)
-        return GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, True)
+        loss = GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, True)
+        self._plan_ahead(key, eng, images, rank or 0, world or 1)
+        return loss
+
+    # The forward above only QUEUES work on the GPU.  Drawing and planning the next call's cutouts right away puts that
+    # host work (~0.3 ms) under the GPU time of this call instead of in front of the next one -- which matters to a
+    # caller that reads the loss back every step.  The draws are the ones the next call would make anyway; if the next
+    # call turns out different (shape, world), the generator is put back to where it was and nothing has changed.
+    def _take_ahead(self, key):
+        ahead, self._ahead = self._ahead, None
+        if ahead is None:
+            return None, None
+        if ahead["key"] == key and ahead["n_cutouts"] == self.n_cutouts and ahead["spec"] == self._cutout_spec():
+            return ahead["rows"], ahead["plan"]
+        self.generator.set_state(ahead["state"])
+        return None, None
+
+    def _cutout_spec(self):
+        return (self.cut_pow, self.min_size, self.max_size)
+
+    def _plan_ahead(self, key, eng, images, rank, world):
+        if not self._own_generator or self.n_cutouts is None:
+            return
+        state = self.generator.get_state()
+        rows = self._cutout_rows(images)
+        self._ahead = {"key": key, "state": state, "rows": rows, "plan": eng.plan_cutouts(rows, rank, world),
+                       "n_cutouts": self.n_cutouts, "spec": self._cutout_spec()}
 
 
 class CLIP(_TextImageLoss):

@@ -251,6 +251,33 @@ def test_module_api_round_trip(cuda_device):
         losses.CLIP("RN50")
 
 
+def test_cutouts_drawn_one_call_ahead_change_nothing(cuda_device):
+    """After a call the module draws and plans the NEXT call's cutouts (host work under the GPU time of this call).  The
+    sequence of cutout tables must be the one the seed gives without looking ahead, also when the next call has another
+    image shape (the generator is put back) and for a caller-supplied generator (never drawn ahead)."""
+    def tables(seed_or_gen, shapes):
+        kw = {"generator": seed_or_gen} if isinstance(seed_or_gen, torch.Generator) else {"seed": seed_or_gen}
+        mod = losses.CLIP("ViT-B-32", n_cutouts=6, min_size=48, **kw)
+        mod.add_encodings_(torch.randn(2, 512, generator=torch.Generator().manual_seed(0)))
+        out = []
+        for hw in shapes:
+            img = torch.rand(2, 3, hw, hw, generator=torch.Generator().manual_seed(hw)).to(cuda_device).requires_grad_()
+            value = mod(img)
+            value.backward()
+            out.append((mod.last_cutouts.copy(), float(value), img.grad.cpu()))
+        return out
+
+    shapes = [96, 96, 128, 96, 96]
+    got = tables(7, shapes)
+    gen = torch.Generator().manual_seed(7)
+    for (rows, _, _), hw in zip(got, shapes):
+        want = np.asarray(sampler_oracle.sample_cutouts(gen, 2, hw, hw, 6, 1.0, 48, None), dtype=np.int32)
+        assert np.array_equal(rows, want)
+    again = tables(torch.Generator().manual_seed(7), shapes)  # a caller's generator: no look-ahead, same results
+    for (r0, v0, g0), (r1, v1, g1) in zip(got, again):
+        assert np.array_equal(r0, r1) and v0 == v1 and torch.equal(g0, g1)
+
+
 def test_full_size_properties_config2(cuda_device):
     """BASELINE.json configs[1] at full size (ViT-B/32, 4 x 512x512, 64 cutouts/image): size-independent
     properties — the loss is the cutout-weighted mean of per-shard losses and the gradient is additive over
