@@ -275,7 +275,8 @@ def test_cutouts_drawn_one_call_ahead_change_nothing(cuda_device):
         assert np.array_equal(rows, want)
     again = tables(torch.Generator().manual_seed(7), shapes)  # a caller's generator: no look-ahead, same results
     for (r0, v0, g0), (r1, v1, g1) in zip(got, again):
-        assert np.array_equal(r0, r1) and v0 == v1 and torch.equal(g0, g1)
+        # (the image gradient is accumulated with red.global.add: same values, run-to-run summation order)
+        assert np.array_equal(r0, r1) and v0 == v1 and torch.allclose(g0, g1, rtol=1e-4, atol=1e-7)
 
 
 def test_full_size_properties_config2(cuda_device):
