@@ -470,9 +470,11 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
     return 0;
 }
 
+// Programmatic dependent launch of the GEMMs (their prologue runs under the previous kernel's tail): on by default,
+// PCG_PDL=0 turns it off.  Same-box A/B: 0.3-0.6 % of a 128-cutout step, ~1 % of a 16-cutout step.
 bool g_pdl_enabled = []() {
     const char* e = getenv("PCG_PDL");
-    return e != nullptr && e[0] == '1';
+    return !(e != nullptr && e[0] == '0');
 }();
 
 // clusters of four that the device keeps resident at once (GPCs with 18 SMs hold four of them and leave a TPC idle)

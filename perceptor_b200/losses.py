@@ -38,7 +38,7 @@ class _TextImageLoss(torch.nn.Module):
         self.max_size = max_size
         self.process_group = process_group
         self.generator = generator if generator is not None else torch.Generator().manual_seed(int(seed))
-        # the module's own generator may be drawn from one call ahead (see _plan_ahead); a caller's generator never is
+        # the module's own generator may be drawn from one call ahead (see _loss); a caller's generator never is
         self._own_generator = generator is None
         self._ahead = None
         self.encodings = None
@@ -99,26 +99,35 @@ class _TextImageLoss(torch.nn.Module):
             rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
         targets = self.encodings.detach().to(eng.device, torch.float32).contiguous()
         tweights = self.weights.detach().to(eng.device, torch.float32).contiguous()
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
         if group is not None and world > 1 and self.shard == "images":
             # image-sharded: every rank passes ITS images (the same count and size on every rank).  The table is drawn
             # for the concatenated batch from the common seed, so the result equals the single-process loss over all
             # ranks' images; a rank's cutouts touch only its own images, so the gradient needs no collective.
             b_local = images.shape[0]
-            rows = self._cutout_rows_for(b_local * world, images.shape[2], images.shape[3])
-            if rows.shape[0] % world != 0:
-                raise ValueError("image-sharded mode needs the same number of cutouts on every rank")
-            self.last_cutouts = rows
-            plan = eng.plan_cutouts(rows, rank, world, b_offset=rank * b_local)
-            return GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, False)
-        key = (tuple(images.shape), rank or 0, world or 1, id(eng), torch.cuda.current_stream(eng.device).cuda_stream)
+            draw = (b_local * world, images.shape[2], images.shape[3])
+            b_offset, reduce_grad = rank * b_local, False
+        else:
+            draw = (images.shape[0], images.shape[2], images.shape[3])
+            b_offset, reduce_grad = None, True
+        key = (draw, rank or 0, world or 1, b_offset, id(eng), stream)
         rows, plan = self._take_ahead(key)
         if rows is None:
-            rows = self._cutout_rows(images)
-            plan = eng.plan_cutouts(rows, rank or 0, world or 1)
+            rows, plan = self._draw_and_plan(eng, draw, rank or 0, world or 1, b_offset)
         self.last_cutouts = rows
-        loss = GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, True)
-        self._plan_ahead(key, eng, images, rank or 0, world or 1)
+        loss = GuidanceLossFn.apply(images, eng, plan, targets, tweights, float(multiplier), group, reduce_grad)
+        if self._own_generator and self.n_cutouts is not None:
+            state = self.generator.get_state()
+            rows, plan = self._draw_and_plan(eng, draw, rank or 0, world or 1, b_offset)
+            self._ahead = {"key": key, "state": state, "rows": rows, "plan": plan, "n_cutouts": self.n_cutouts,
+                           "spec": self._cutout_spec()}
         return loss
+
+    def _draw_and_plan(self, eng, draw, rank, world, b_offset):
+        rows = self._cutout_rows_for(*draw)
+        if b_offset is not None and rows.shape[0] % world != 0:
+            raise ValueError("image-sharded mode needs the same number of cutouts on every rank")
+        return rows, eng.plan_cutouts(rows, rank, world, b_offset=b_offset)
 
     # The forward above only QUEUES work on the GPU.  Drawing and planning the next call's cutouts right away puts that
     # host work (~0.3 ms) under the GPU time of this call instead of in front of the next one -- which matters to a
@@ -135,14 +144,6 @@ class _TextImageLoss(torch.nn.Module):
 
     def _cutout_spec(self):
         return (self.cut_pow, self.min_size, self.max_size)
-
-    def _plan_ahead(self, key, eng, images, rank, world):
-        if not self._own_generator or self.n_cutouts is None:
-            return
-        state = self.generator.get_state()
-        rows = self._cutout_rows(images)
-        self._ahead = {"key": key, "state": state, "rows": rows, "plan": eng.plan_cutouts(rows, rank, world),
-                       "n_cutouts": self.n_cutouts, "spec": self._cutout_spec()}
 
 
 class CLIP(_TextImageLoss):
