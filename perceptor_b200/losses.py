@@ -119,8 +119,8 @@ class _TextImageLoss(torch.nn.Module):
         if self._own_generator and self.n_cutouts is not None:
             state = self.generator.get_state()
             rows, plan = self._draw_and_plan(eng, draw, rank or 0, world or 1, b_offset)
-            self._ahead = {"key": key, "state": state, "rows": rows, "plan": plan, "n_cutouts": self.n_cutouts,
-                           "spec": self._cutout_spec()}
+            self._ahead = {"key": key, "state": state, "state_after": self.generator.get_state(), "rows": rows,
+                           "plan": plan, "n_cutouts": self.n_cutouts, "spec": self._cutout_spec()}
         return loss
 
     def _draw_and_plan(self, eng, draw, rank, world, b_offset):
@@ -132,11 +132,15 @@ class _TextImageLoss(torch.nn.Module):
     # The forward above only QUEUES work on the GPU.  Drawing and planning the next call's cutouts right away puts that
     # host work (~0.3 ms) under the GPU time of this call instead of in front of the next one -- which matters to a
     # caller that reads the loss back every step.  The draws are the ones the next call would make anyway; if the next
-    # call turns out different (shape, world), the generator is put back to where it was and nothing has changed.
+    # call turns out different (shape, world), the generator is put back to where it was and nothing has changed; if the
+    # caller has touched `self.generator` in between (reseeded it, drawn from it), the look-ahead is dropped and the
+    # generator is used as found.  (A state saved with `generator.get_state()` after a call is one draw ahead.)
     def _take_ahead(self, key):
         ahead, self._ahead = self._ahead, None
         if ahead is None:
             return None, None
+        if not torch.equal(self.generator.get_state(), ahead["state_after"]):
+            return None, None  # the caller reseeded (or drew from) the generator since: its state is the one that counts
         if ahead["key"] == key and ahead["n_cutouts"] == self.n_cutouts and ahead["spec"] == self._cutout_spec():
             return ahead["rows"], ahead["plan"]
         self.generator.set_state(ahead["state"])

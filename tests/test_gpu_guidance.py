@@ -273,6 +273,15 @@ def test_cutouts_drawn_one_call_ahead_change_nothing(cuda_device):
     for (rows, _, _), hw in zip(got, shapes):
         want = np.asarray(sampler_oracle.sample_cutouts(gen, 2, hw, hw, 6, 1.0, 48, None), dtype=np.int32)
         assert np.array_equal(rows, want)
+    # reseeding the module's generator between calls takes effect at once (the look-ahead is dropped)
+    mod = losses.CLIP("ViT-B-32", n_cutouts=6, min_size=48, seed=3)
+    mod.add_encodings_(torch.randn(2, 512, generator=torch.Generator().manual_seed(0)))
+    img = torch.rand(2, 3, 96, 96, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    with torch.no_grad():
+        mod(img)
+        mod.generator.manual_seed(7)
+        mod(img)
+    assert np.array_equal(mod.last_cutouts, got[0][0])
     again = tables(torch.Generator().manual_seed(7), shapes)  # a caller's generator: no look-ahead, same results
     for (r0, v0, g0), (r1, v1, g1) in zip(got, again):
         # (the image gradient is accumulated with red.global.add: same values, run-to-run summation order)
