@@ -1969,6 +1969,45 @@ __device__ __noinline__ void bwd_epilogue2(uint32_t taddr_a, float coef_a, const
     }
 }
 
+// One 64-column accumulator (dV_j, dK_j or dQ_i) of this warp's 32 rows -> bf16, through a 4 KB swizzled staging tile and
+// ONE bulk tensor store.  Storing rows straight from the tensor-memory layout (bwd_epilogue2 above: thread = row, 16
+// bytes per lane and instruction) costs 32 L1 wavefronts per store instruction -- 6144 per item, ~12 000 clk of the
+// load/store unit at the measured 2 clk per wavefront, which the elementwise and edge warps queue behind; the staging
+// tile takes 4 wavefronts per instruction and the TMA engine writes whole lines.  Rows >= nv are clipped by the map.
+__device__ __noinline__ void bwd_drain_tma(uint32_t taddr, float coef, const float* xrow, uint8_t* stage, const CUtensorMap* map,
+                                           int col, int row0, int n, int lane) {
+    uint32_t va[32], vb[32];
+    tmem_ld<32>(taddr, va);
+    tmem_ld<32>(taddr + 32, vb);
+    tmem_wait_ld();
+    if (lane == 0) bulk_wait_read_all();  // the previous store of this warp has read the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t(&v)[32] = half == 0 ? va : vb;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 xa = *reinterpret_cast<const float4*>(xrow + half * 32 + g * 8);
+            const float4 xb = *reinterpret_cast<const float4*>(xrow + half * 32 + g * 8 + 4);
+            const uint4 o = make_uint4(pack_bf16(fmaf(coef, xa.x, __uint_as_float(v[8 * g])),
+                                                 fmaf(coef, xa.y, __uint_as_float(v[8 * g + 1]))),
+                                       pack_bf16(fmaf(coef, xa.z, __uint_as_float(v[8 * g + 2])),
+                                                 fmaf(coef, xa.w, __uint_as_float(v[8 * g + 3]))),
+                                       pack_bf16(fmaf(coef, xb.x, __uint_as_float(v[8 * g + 4])),
+                                                 fmaf(coef, xb.y, __uint_as_float(v[8 * g + 5]))),
+                                       pack_bf16(fmaf(coef, xb.z, __uint_as_float(v[8 * g + 6])),
+                                                 fmaf(coef, xb.w, __uint_as_float(v[8 * g + 7]))));
+            *reinterpret_cast<uint4*>(stage + row_chunk(lane, half * 4 + g)) = o;
+        }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_3d(map, stage, col, row0, n);
+        bulk_commit_group();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // backward, persistent (the production kernel for 130 <= T <= 257: two key tiles, two query blocks)
 // ---------------------------------------------------------------------------------------------------------
@@ -1994,7 +2033,9 @@ constexpr int kPbOffVec = 12 * kBlkBytes;                 // 2 slots x float[256
 constexpr int kPbOffX = kPbOffVec + 2 * 6 * 1024;         // 2 slots x {float[64] x 4: q_x, k_x, v_x, dO_x; 8 scalars}
 constexpr int kPbXFloats = 4 * 64 + 8;
 constexpr int kPbOffBar = kPbOffX + 2 * kPbXFloats * 4;
-constexpr int kPbSmemBytes = kPbOffBar + 20 * 8 + 64 + 1024;  // <= 20 mbarriers + tmem slot
+constexpr int kPbOffStage = (kPbOffBar + 20 * 8 + 64 + 1023) / 1024 * 1024;  // <= 20 mbarriers + tmem slot; then 4 x 4 KB
+constexpr int kPbSmemBytes = kPbOffStage + kPbDrain * 4096 + 1024;           // drain staging tiles (128-byte swizzle)
+static_assert(kPbSmemBytes <= 232448, "persistent backward exceeds the 227 KB dynamic shared memory limit");
 enum {
     kPbFullK0 = 0, kPbFullV0 = 1, kPbFullQD0 = 2, kPbFull1 = 3,  // operand tiles landed (TMA)
     kPbSReady = 4,      // S^T / dP^T of a block retired                       (per block)
@@ -2027,7 +2068,7 @@ struct PbParams {
 
 __global__ void __launch_bounds__(kPbThreads, 1)
 attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
-                        const PbParams p) {
+                        const __grid_constant__ CUtensorMap map_dqkv, const PbParams p) {
     grid_dep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -2412,6 +2453,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
             const int dw = warp - 9 - kPbEdge;  // 0..3
             const int quarter = warp & 3;        // tensor-memory lane quarter this warp may read (12..15 -> 0..3)
             const uint32_t trow = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+            uint8_t* stage = sm + kPbOffStage + dw * 4096;
             // delta = rowsum(dO * O) of item `it` into its slot: eight lanes share a 128-byte row, four rows per step,
             // 16 steps per warp in two batches of eight loads in flight
             auto prepare_delta = [&](int it) {
@@ -2470,11 +2512,8 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
                     tc_fence_after();
                     if (tr) p.trace[cta_id * 32 + 14 + 4 * j] = clock64();
                     const int row0 = j * 128 + quarter * 32;
-#pragma unroll 1
-                    for (int ph = 0; ph < 2; ++ph)
-                        bwd_epilogue2(trow + kColDV + ph * 32, prow[row0 + lane], dox + ph * 32, gd + 2 * D + ph * 32, row0,
-                                      trow + kColDK + ph * 32, dsrow[row0 + lane], qx + ph * 32, gd + D + ph * 32, row0, lane,
-                                      static_cast<size_t>(3) * D, nv);
+                    bwd_drain_tma(trow + kColDV, prow[row0 + lane], dox, stage, &map_dqkv, 2 * D + h * kHd, row0, n, lane);
+                    bwd_drain_tma(trow + kColDK, dsrow[row0 + lane], qx, stage, &map_dqkv, D + h * kHd, row0, n, lane);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars[kPbAccFreeVK]);
@@ -2482,16 +2521,15 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
                 }
                 mbar_wait_c(&bars[kPbDqDone], ip);
                 tc_fence_after();
-#pragma unroll 1
-                for (int ph = 0; ph < 2; ++ph)
-                    bwd_epilogue2(trow + kColDQ + ph * 32, dscol[quarter * 32 + lane], kx + ph * 32, gd + ph * 32, quarter * 32,
-                                  trow + kColDQ + 64 + ph * 32, dscol[128 + quarter * 32 + lane], kx + ph * 32, gd + ph * 32,
-                                  128 + quarter * 32, lane, static_cast<size_t>(3) * D, nv);
+                bwd_drain_tma(trow + kColDQ, dscol[quarter * 32 + lane], kx, stage, &map_dqkv, h * kHd, quarter * 32, n, lane);
+                bwd_drain_tma(trow + kColDQ + 64, dscol[128 + quarter * 32 + lane], kx, stage, &map_dqkv, h * kHd,
+                              128 + quarter * 32, n, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[kPbAccFreeQ]), mbar_arrive(&bars[kPbSlotFree + s]);
                 if (tr) p.trace[cta_id * 32 + 17] = clock64();
             }
+            if (lane == 0) bulk_wait_all();  // this warp's bulk stores have left shared memory and completed
         }
     }
     tc_fence_before();
@@ -3045,22 +3083,27 @@ EncodeFn encode_fn() {
 
 // [n][T][cols] bf16 view of a row-major [n*T, cols] matrix; box = {64 columns, box_rows (128 or 64) rows, 1}.
 // Rows >= T of a box are zero-filled, so whole boxes are always loaded.
-int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols, int box_rows = 128) {
+// `rows_dim` (default T): the extent of the row dimension when it is shorter than the stride between cutouts -- a store
+// map that must not touch the last token's row.
+int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols, int box_rows = 128, int rows_dim = 0) {
+    if (rows_dim <= 0) rows_dim = T;
     struct Key {
         const void* p;
-        int n, T, cols, box;
-        bool operator==(const Key& o) const { return p == o.p && n == o.n && T == o.T && cols == o.cols && box == o.box; }
+        int n, T, cols, box, rows;
+        bool operator==(const Key& o) const {
+            return p == o.p && n == o.n && T == o.T && cols == o.cols && box == o.box && rows == o.rows;
+        }
     };
     struct Hash {
         size_t operator()(const Key& k) const {
             size_t h = reinterpret_cast<size_t>(k.p);
-            for (int v : {k.n, k.T, k.cols, k.box}) h = h * 1000003u ^ static_cast<size_t>(v);
+            for (int v : {k.n, k.T, k.cols, k.box, k.rows}) h = h * 1000003u ^ static_cast<size_t>(v);
             return h;
         }
     };
     static std::mutex mu;
     static std::unordered_map<Key, CUtensorMap, Hash> cache;
-    const Key key{ptr, n, T, cols, box_rows};
+    const Key key{ptr, n, T, cols, box_rows, rows_dim};
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
@@ -3071,7 +3114,7 @@ int make_map3(CUtensorMap* out, const void* ptr, int n, int T, int cols, int box
     }
     EncodeFn encode = encode_fn();
     if (encode == nullptr) return set_error(-2, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
-    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(n)};
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows_dim), static_cast<cuuint64_t>(n)};
     const cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(cols) * 2 * T};
     const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
@@ -3286,8 +3329,11 @@ extern "C" int pcg_attn_bwd(const void* qkv, const void* out, const void* d_out,
         PCG_CHECK_ARG(items < (1ll << 30), "pcg_attn_bwd: too many (cutout, head) items");
         PbParams pb{T, heads, nv, static_cast<int>(items), static_cast<const bf16*>(qkv), static_cast<const bf16*>(out),
                     static_cast<const bf16*>(d_out), lse, static_cast<bf16*>(d_qkv), g_trace};
+        // store map of d_qkv: rows [0, nv) of every cutout (the edge token's row is written by the edge warps), 32-row boxes
+        CUtensorMap map_dqkv;
+        if (int rc = make_map3(&map_dqkv, d_qkv, n, T, 3 * D, 32, nv)) return rc;
         const int grid = static_cast<int>(std::min<long long>(items, sm_count()));
-        attn_bwd_persist_kernel<<<grid, kPbThreads, kPbSmemBytes, s>>>(map, map_do, pb);
+        attn_bwd_persist_kernel<<<grid, kPbThreads, kPbSmemBytes, s>>>(map, map_do, map_dqkv, pb);
         PCG_LAUNCH_CHECK("attn_bwd_persist_kernel");
         return 0;
     }

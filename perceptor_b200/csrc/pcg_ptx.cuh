@@ -227,6 +227,20 @@ __device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, voi
         : "memory");
 }
 
+// 3-D tiled TMA STORE of a shared-memory box (bulk async-group completion); rows / columns outside the tensor map's
+// extents are clipped.  The writers of the box fence_proxy_async() + synchronise before one thread issues this.
+__device__ __forceinline__ void tma_store_3d(const void* desc, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's committed bulk stores have READ their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // TMA prefetch of one box into L2 (no shared memory, no barrier): used to pull the operands of the CTA that will
 // run on this SM next, so its loads hit L2 instead of queueing on HBM with every other SM's.
 __device__ __forceinline__ void tma_prefetch_3d(const void* desc, int32_t c0, int32_t c1, int32_t c2) {
