@@ -981,7 +981,8 @@ __device__ __forceinline__ float exp32_f2(const uint32_t (&v)[32], float mb, uin
 }
 
 __global__ void __launch_bounds__(kFwd3Threads, 2)
-attn_fwd_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd3Params p) {
+attn_fwd_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out,
+                      const Fwd3Params p) {
     grid_dep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -1207,8 +1208,11 @@ attn_fwd_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd3Par
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kB2TmemFree]);
-            bf16* grow = p.out + (static_cast<size_t>(n) * p.T + q0 + r) * D + h * kHd + 32 * grp;
-            const bool row_ok = q0 + r < nv;
+            // The O tile goes out through this item's Q slot (dead: S has retired and every warp has taken its edge score)
+            // as a 128-byte-swizzled [128 x 64] bf16 tile and one bulk tensor store per lane quarter.  Rows stored
+            // straight from the tensor-memory layout cost 32 L1 wavefronts per store instruction, which the other
+            // resident CTA's warps queue behind; rows >= nv are clipped by the store map.
+            uint8_t* stage = sm_q0 + s * kBlkBytes;
             const float* vxg = vx + 32 * grp;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -1222,13 +1226,23 @@ attn_fwd_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const Fwd3Par
                                                      fmaf(px, xb.y, __uint_as_float(va[8 * g + 5])) * inv),
                                            pack_bf16(fmaf(px, xb.z, __uint_as_float(va[8 * g + 6])) * inv,
                                                      fmaf(px, xb.w, __uint_as_float(va[8 * g + 7])) * inv));
-                if (row_ok) *reinterpret_cast<uint4*>(grow + g * 8) = o;
+                *reinterpret_cast<uint4*>(stage + row_chunk(r, 4 * grp + g)) = o;
+            }
+            fence_proxy_async();
+            named_bar_sync(1 + quarter, 64);  // both column halves of rows [32 quarter, +32) are in the tile
+            if (grp == 0) {
+                if (lane == 0) {
+                    tma_store_3d(&map_out, stage + quarter * 4096, h * kHd, q0 + 32 * quarter, n);
+                    bulk_commit_group();
+                    bulk_wait_read_all();  // the slot may be refilled once the store has read it
+                }
+                __syncwarp();
             }
             // this item's Q slot and edge vectors (v_x above was their last reader in this warp) may be refilled
-            __syncwarp();
             if (lane == 0) mbar_arrive(&bars[kB2Done + s]);
             if (tr) p.trace[cta_id * 32 + (grp == 0 ? 8 : 19)] = clock64();
         }
+        if (grp == 0 && lane == 0) bulk_wait_all();
     } else {
         // edge warp: as in attn_fwd_persist_kernel
 #pragma unroll 1
@@ -3241,7 +3255,10 @@ extern "C" int pcg_attn_fwd(const void* qkv, void* out, float* lse, int n, int T
                                                   static_cast<bf16*>(out), lse, g_trace, 0};
         p3.heads_magic = static_cast<uint32_t>(((1ull << 32) + heads - 1) / heads);
         p3.grid_magic = static_cast<uint32_t>(((1ull << 32) + grid - 1) / grid);
-        attn_fwd_split_kernel<<<grid, kFwd3Threads, kFwd3SmemBytes, s>>>(map, p3);
+        // store map of the output: rows [0, nv) of every cutout (the edge token's row is the edge warp's), 32-row boxes
+        CUtensorMap map_out;
+        if (int rc = make_map3(&map_out, out, n, T, D, 32, nv)) return rc;
+        attn_fwd_split_kernel<<<grid, kFwd3Threads, kFwd3SmemBytes, s>>>(map, map_out, p3);
         PCG_LAUNCH_CHECK("attn_fwd_split_kernel");
         return 0;
     }
