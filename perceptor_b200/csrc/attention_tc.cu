@@ -965,6 +965,27 @@ struct Fwd3Params : Fwd2Params {
     uint32_t heads_magic, grid_magic;  // ceil(2^32 / heads), ceil(2^32 / gridDim.x): exact quotients for the sizes the host admits
 };
 
+// Every kPolyEvery-th PAIR of exponentials is taken on the FMA / ALU pipes instead of MUFU (which is what the exp pass
+// waits for: four softmax warps per scheduler, 16 ex2 per clock and SM): Cody-Waite split a = n + f with the round-to-
+// nearest magic constant, 2^f on [-0.5, 0.5] as a cubic (relative error 7.5e-5; the result is rounded to bf16, 3.9e-3),
+// 2^n added into the exponent field.  Packed fp32 arithmetic: 3 FMA-pipe + 2 ALU instructions per element.
+#ifndef PCG_ATTN_POLY_EVERY
+#define PCG_ATTN_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = PCG_ATTN_POLY_EVERY;
+__device__ __forceinline__ float2 exp2_poly2(float2 a) {
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    a.x = fmaxf(a.x, -120.f), a.y = fmaxf(a.y, -120.f);  // -inf (masked column) and underflow: 2^-120 rounds to 0 in the sum
+    const float2 t = __fadd2_rn(a, magic);
+    const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __fadd2_rn(a, make_float2(-n.x, -n.y));
+    float2 p = __ffma2_rn(f, make_float2(0.05517165f, 0.05517165f), make_float2(0.24261112f, 0.24261112f));
+    p = __ffma2_rn(p, f, make_float2(0.69326099f, 0.69326099f));
+    p = __ffma2_rn(p, f, make_float2(0.99992807f, 0.99992807f));
+    return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                       __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+}
+
 __device__ __forceinline__ float exp32_f2(const uint32_t (&v)[32], float mb, uint32_t tdst, float sum) {
     uint32_t pk[16];
     float2 s01 = make_float2(0.f, 0.f);
@@ -972,7 +993,9 @@ __device__ __forceinline__ float exp32_f2(const uint32_t (&v)[32], float mb, uin
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float2 a = __ffma2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), l2, nmb);
-        const float2 e = make_float2(exp2f(a.x), exp2f(a.y));
+        const float2 e = (kPolyEvery > 0 && j % (kPolyEvery > 0 ? kPolyEvery : 1) == kPolyEvery - 1)
+                             ? exp2_poly2(a)
+                             : make_float2(exp2f(a.x), exp2f(a.y));
         s01 = __fadd2_rn(s01, e);
         pk[j] = pack_bf16(e.x, e.y);
     }
