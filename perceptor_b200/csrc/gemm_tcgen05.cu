@@ -114,9 +114,18 @@ __device__ __forceinline__ float2 act_and_grad2(float2 h, float2& grad) {
 // instead of 16 + 16.  (The GEMMs of the step sit at the L2's practical throughput: their rates follow
 // operand + epilogue bytes per tile, see DESIGN.md.)  A stage may be refilled once BOTH pairs' MMAs have read it: the
 // empty barriers collect one tcgen05.commit from each pair leader.
+// PCG_GEMM_TS (compile time): the bf16-output epilogues (BF16, BIAS_ACT) keep the tensor-memory layout (thread = row),
+// write packed bf16 rows into two 2 KB staging tiles per warp (64-byte swizzle) and send them out with bulk tensor
+// stores, instead of transposing fp32 through shared memory for coalesced st.global: per 32-column chunk and warp that
+// is 16-32 L1 wavefronts instead of 96-128.
+#ifndef PCG_GEMM_TS
+#define PCG_GEMM_TS 1
+#endif
+
 template <int BN, int MODE, int ACT, int CTAS, bool MC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_o2,
                     const GemmParams p) {
     static_assert(!MC || CTAS == 2, "multicast clusters are built from CTA pairs");
     using Cfg = TileCfg<BN, CTAS>;
@@ -264,6 +273,86 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
             }
         }
+    } else if (warp < kEpiWarps && PCG_GEMM_TS && (MODE == PCG_GEMM_BF16 || MODE == PCG_GEMM_BIAS_ACT)) {
+        // ===================== epilogue with bulk tensor stores (thread = row throughout) =====================
+        const int quarter = warp & 3, half = warp >> 2;
+        constexpr int kHalfN = BN / 2, kChunks = kHalfN / 32;
+        uint8_t* buf0 = smem_epi + warp * kEpiStageBytes;  // [32 rows x 64 B], 16-byte chunk k of row r at k ^ ((r >> 1) & 3)
+        uint8_t* buf1 = buf0 + 2048;
+        const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+        int it = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int row_base = tile_m(tile) * kTileM + cta_rank * BM + quarter * 32;
+            const int col_base = tile_n(tile) * BN + half * kHalfN;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * kHalfN;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr0, r);
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int col0 = col_base + c * 32;
+                float4 b4[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)  // the same 16 bytes for every lane: one wavefront, an L1 hit after the first warp
+                    b4[j] = (p.bias != nullptr && col0 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                tmem_wait_ld();
+                uint32_t pk[16], pg[MODE == PCG_GEMM_BIAS_ACT ? 16 : 1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 v01 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
+                                                  make_float2(b4[j].x, b4[j].y));
+                    const float2 v23 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
+                                                  make_float2(b4[j].z, b4[j].w));
+                    if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
+                        float2 g01, g23;
+                        const float2 a01 = act_and_grad2<ACT>(v01, g01);
+                        const float2 a23 = act_and_grad2<ACT>(v23, g23);
+                        pk[2 * j] = pack_bf16(a01.x, a01.y), pk[2 * j + 1] = pack_bf16(a23.x, a23.y);
+                        pg[2 * j] = pack_bf16(g01.x, g01.y), pg[2 * j + 1] = pack_bf16(g23.x, g23.y);
+                    } else {
+                        pk[2 * j] = pack_bf16(v01.x, v01.y), pk[2 * j + 1] = pack_bf16(v23.x, v23.y);
+                    }
+                }
+                if (c + 1 < kChunks) {
+                    tmem_ld_32x32(taddr0 + (c + 1) * 32, r);  // in flight while this chunk goes out
+                } else {
+                    // the accumulator is in registers: the MMA thread may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CTAS == 2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);
+                    }
+                }
+                // Two staging tiles, every store its own bulk group.  A tile may be rewritten once the store issued from it
+                // two groups ago has read it -- "at most one group pending": BF16 alternates between the tiles from chunk
+                // to chunk, BIAS_ACT sends act'(h) through tile 0 and act(h) through tile 1 in every chunk.
+                auto put = [&](uint8_t* dst, const uint32_t* q, const CUtensorMap* map) {
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<uint4*>(dst + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(k) ^ sw) << 4)) =
+                            make_uint4(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && col0 < p.N) {
+                        tma_store_2d(map, dst, col0, row_base);
+                        bulk_commit_group();
+                    }
+                };
+                if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
+                    put(buf0, pg, &map_o);   // out  = act'(h)
+                    put(buf1, pk, &map_o2);  // out2 = act(h)
+                } else {
+                    put((c & 1) == 0 ? buf0 : buf1, pk, &map_o);
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
     } else if (warp < kEpiWarps) {
         // TMEM -> registers (thread = row) -> XOR-swizzled per-warp staging tile in smem -> registers
         // (8 lanes = one row's 32 columns) so that every global access is a full, coalesced row segment.
@@ -440,6 +529,37 @@ struct MapKeyHash {
     }
 };
 
+// store map of a bf16 [rows, cols] output (row stride ld): 32 x 32 boxes, 64-byte swizzle (PCG_GEMM_TS epilogue)
+int get_store_map(CUtensorMap* out, const void* ptr, int rows, int cols, int ld) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, rows, cols, ld, -32};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return 0;
+        }
+    }
+    EncodeFn encode = get_encode_fn();
+    if (encode == nullptr) return set_error(-2, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(-3, "cuTensorMapEncodeTiled(store) failed (CUresult %d) rows=%d cols=%d ld=%d ptr=%p",
+                         static_cast<int>(r), rows, cols, ld, ptr);
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return 0;
+}
+
 int get_tensor_map(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
@@ -498,7 +618,8 @@ int max_clusters_of_4(Kernel kernel, int smem, int* out) {
 }
 
 template <int BN, int MODE, int ACT, int CTAS, bool MC = false>
-int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mo2,
+                  const GemmParams& p, cudaStream_t stream) {
     using Cfg = TileCfg<BN, CTAS>;
     constexpr int kCluster = CTAS * (MC ? 2 : 1);
     static PerDeviceOnce configured;
@@ -538,26 +659,28 @@ int launch_gemm_a(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     }
     cfg.attrs = attr;
     cfg.numAttrs = n_attr;
-    PCG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, ACT, CTAS, MC>, ma, mb, p));
+    PCG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, ACT, CTAS, MC>, ma, mb, mo, mo2, p));
     PCG_LAUNCH_CHECK("gemm_tcgen05_kernel");
     return 0;
 }
 template <int BN, int MODE, int CTAS, bool MC = false>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mo2,
+                const GemmParams& p, cudaStream_t stream) {
     if constexpr (MODE == PCG_GEMM_BIAS_ACT) {
-        if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU, CTAS, MC>(ma, mb, p, stream);
+        if (p.act == PCG_ACT_GELU) return launch_gemm_a<BN, MODE, PCG_ACT_GELU, CTAS, MC>(ma, mb, mo, mo2, p, stream);
     }
-    return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU, CTAS, MC>(ma, mb, p, stream);
+    return launch_gemm_a<BN, MODE, PCG_ACT_QUICKGELU, CTAS, MC>(ma, mb, mo, mo2, p, stream);
 }
 
 template <int BN, int CTAS = 1, bool MC = false>
-int dispatch_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+int dispatch_mode(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mo2,
+                  const GemmParams& p, cudaStream_t s) {
     switch (mode) {
-        case PCG_GEMM_BF16: return launch_gemm<BN, PCG_GEMM_BF16, CTAS, MC>(ma, mb, p, s);
-        case PCG_GEMM_BIAS_ACT: return launch_gemm<BN, PCG_GEMM_BIAS_ACT, CTAS, MC>(ma, mb, p, s);
-        case PCG_GEMM_RESID_F32: return launch_gemm<BN, PCG_GEMM_RESID_F32, CTAS, MC>(ma, mb, p, s);
-        case PCG_GEMM_DACT: return launch_gemm<BN, PCG_GEMM_DACT, CTAS, MC>(ma, mb, p, s);
-        case PCG_GEMM_F32: return launch_gemm<BN, PCG_GEMM_F32, CTAS, MC>(ma, mb, p, s);
+        case PCG_GEMM_BF16: return launch_gemm<BN, PCG_GEMM_BF16, CTAS, MC>(ma, mb, mo, mo2, p, s);
+        case PCG_GEMM_BIAS_ACT: return launch_gemm<BN, PCG_GEMM_BIAS_ACT, CTAS, MC>(ma, mb, mo, mo2, p, s);
+        case PCG_GEMM_RESID_F32: return launch_gemm<BN, PCG_GEMM_RESID_F32, CTAS, MC>(ma, mb, mo, mo2, p, s);
+        case PCG_GEMM_DACT: return launch_gemm<BN, PCG_GEMM_DACT, CTAS, MC>(ma, mb, mo, mo2, p, s);
+        case PCG_GEMM_F32: return launch_gemm<BN, PCG_GEMM_F32, CTAS, MC>(ma, mb, mo, mo2, p, s);
         default: return set_error(-1, "pcg_gemm_bf16: unknown mode %d", mode);
     }
 }
@@ -633,15 +756,24 @@ int gemm_bf16_impl(int mode, int act, int M, int N, int K, const void* A, int ld
     if (rc) return rc;
     rc = get_tensor_map(&mb, B, N, K, ldb, pair ? 128 : bn);
     if (rc) return rc;
+    CUtensorMap mo = ma, mo2 = ma;  // placeholders unless the bulk-store epilogue is compiled in and applies
+    if (PCG_GEMM_TS && (mode == PCG_GEMM_BF16 || mode == PCG_GEMM_BIAS_ACT)) {
+        rc = get_store_map(&mo, out, M, N, ldo);
+        if (rc) return rc;
+        if (mode == PCG_GEMM_BIAS_ACT) {
+            rc = get_store_map(&mo2, out2, M, N, ldo);
+            if (rc) return rc;
+        }
+    }
     GemmParams p{M, N, K, bias, aux, out, out2, ldo, act};
     ProfileScope prof(PCG_PROF_GEMM, 2.0 * M * N * K, stream);
-    if (mc) return dispatch_mode<256, 2, true>(mode, ma, mb, p, stream);
-    if (pair) return dispatch_mode<256, 2>(mode, ma, mb, p, stream);
+    if (mc) return dispatch_mode<256, 2, true>(mode, ma, mb, mo, mo2, p, stream);
+    if (pair) return dispatch_mode<256, 2>(mode, ma, mb, mo, mo2, p, stream);
     switch (bn) {
-        case 256: return dispatch_mode<256>(mode, ma, mb, p, stream);
-        case 192: return dispatch_mode<192>(mode, ma, mb, p, stream);
-        case 128: return dispatch_mode<128>(mode, ma, mb, p, stream);
-        case 64: return dispatch_mode<64>(mode, ma, mb, p, stream);
+        case 256: return dispatch_mode<256>(mode, ma, mb, mo, mo2, p, stream);
+        case 192: return dispatch_mode<192>(mode, ma, mb, mo, mo2, p, stream);
+        case 128: return dispatch_mode<128>(mode, ma, mb, mo, mo2, p, stream);
+        case 64: return dispatch_mode<64>(mode, ma, mb, mo, mo2, p, stream);
         default: return set_error(-1, "pcg_gemm_bf16: unsupported BN %d", bn);
     }
 }
