@@ -43,11 +43,10 @@ DEFAULT_WORKLOAD = "vit_l14_224_128cut_512px"
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per gemm_tcgen05_kernel launch, mean over the eight GEMM
 # shapes of one transformer layer (forward qkv / out / fc / proj, backward dproj / dfc / dout / dqkv), READ from the
 # committed `ncu --set full` summaries (tools/ncu_summ.py output) rather than typed in.
-# (file, first GEMM row, rows): tools/profile_r02c.sh captures eight consecutive GEMM launches of the timed step's forward
-# (layers 10, 11: qkv, out, fc, proj twice) and eight of its backward (layers 17, 16: dproj, dfc, dout, dqkv twice); the
-# first four rows of each file are one layer
-NCU_GEMM_TRAFFIC_FILES = {"vit_l14_224_128cut_512px": (("profiles/r02c_gemm_fwd_ncu_full.csv", 0, 4),
-                                                       ("profiles/r02c_gemm_bwd_ncu_full.csv", 0, 4))}
+# (file, first GEMM row, rows): tools/profile_r02e.sh captures four consecutive GEMM launches of the timed step's forward
+# (layer 10: qkv, out, fc, proj) and four of its backward (layer 17: dproj, dfc, dout, dqkv)
+NCU_GEMM_TRAFFIC_FILES = {"vit_l14_224_128cut_512px": (("profiles/r02e_gemm_fwd_ncu_full.csv", 0, 4),
+                                                       ("profiles/r02e_gemm_bwd_ncu_full.csv", 0, 4))}
 
 
 def ncu_gemm_traffic(workload: str):
