@@ -280,6 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint8_t* buf0 = smem_epi + warp * kEpiStageBytes;  // [32 rows x 64 B], 16-byte chunk k of row r at k ^ ((r >> 1) & 3)
         uint8_t* buf1 = buf0 + 2048;
         const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+        [[maybe_unused]] uint32_t n_put = 0;
         int it = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
@@ -348,7 +349,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     put(buf0, pg, &map_o);   // out  = act'(h)
                     put(buf1, pk, &map_o2);  // out2 = act(h)
                 } else {
-                    put((c & 1) == 0 ? buf0 : buf1, pk, &map_o);
+                    // (a running count, not the chunk index: with an odd number of chunks per tile -- BN = 64, 192 -- the
+                    // first chunk of the next tile would otherwise reuse the tile that the store just before it reads)
+                    put((n_put++ & 1) == 0 ? buf0 : buf1, pk, &map_o);
                 }
             }
         }
