@@ -125,6 +125,39 @@ def test_shapes_and_flop_model_match_baseline_table():
     assert sd["conv1.weight"].shape == (768, 3, 32, 32) and sd["proj"].shape == (768, 512)
 
 
+def test_executed_flop_model_of_the_class_token_last_block():
+    """flops_per_cutout(pooled_last_block=True) counts what the default sequencer executes: the last block keeps only its
+    K / V projections (and the full dqkv dgrad GEMM) on every token; counted by hand for ViT-L/14."""
+    s = SHAPES["ViT-L-14"]
+    t, d, mlp = s.tokens, s.width, s.mlp
+    per_token = 8 * d * d + 4 * d * mlp
+    dense, pooled = s.flops_per_cutout(), s.flops_per_cutout(pooled_last_block=True)
+    saved_fwd = t * per_token - (t * 4 * d * d + (4 * d * d + 4 * d * mlp)) + 4 * t * t * d - 4 * t * d
+    saved_bwd = t * per_token - (t * 6 * d * d + (2 * d * d + 4 * d * mlp)) + 8 * t * t * d - 8 * t * d
+    assert abs((dense - pooled) - (saved_fwd + saved_bwd)) <= 1e-6 * dense
+    assert 0.96 < pooled / dense < 0.97  # 3.3 % of the step for ViT-L/14
+    for name in SHAPES:
+        assert SHAPES[name].flops_per_cutout(True) < SHAPES[name].flops_per_cutout()
+
+
+def test_resize_table_ids_from_the_lookup_array():
+    """GuidanceEngine._table_ids_for_sizes (the per-step host path) against ResizeTableCache.table_id, on a stub engine:
+    first use fills the lookup array, sizes beyond it grow it, ids stay those of the cache."""
+    from types import SimpleNamespace
+
+    from perceptor_b200.guidance import GuidanceEngine
+    from perceptor_b200.resize_tables import ResizeTableCache
+
+    stub = SimpleNamespace(tables=ResizeTableCache(32), shape=SimpleNamespace(image_size=32))
+    stub._method_for_size = lambda size: GuidanceEngine._method_for_size(stub, size)
+    rng = np.random.default_rng(0)
+    for top in (40, 40, 1500):
+        sizes = rng.integers(8, top, size=64).astype(np.int32)
+        got = GuidanceEngine._table_ids_for_sizes(stub, sizes)
+        want = np.array([stub.tables.table_id(int(v), stub._method_for_size(int(v))) for v in sizes], dtype=np.int32)
+        assert got.dtype == np.int32 and np.array_equal(got, want)
+
+
 def test_module_surface_and_error_behaviour_without_gpu(tmp_path):
     with pytest.raises(ValueError):
         models.OpenCLIP("ViT-B-32", "not-a-weight-name")
