@@ -234,7 +234,9 @@ int pcg_guidance_bwd(const pcg_guidance_args *a, void *stream);
  * pcg_guidance_fwd / _bwd run the last block's attention output, out-projection, ln_2 and MLP on the n class-token rows
  * instead of all n*T rows (K and V projections, ln_1 and everything below stay full): the same loss and image gradient
  * from 10/12 of one block's GEMM work less.  on = 0 restores the full last block (also: PCG_FULL_LAST_BLOCK=1 in the
- * environment); returns the previous setting.  Takes effect for subsequent calls (captured CUDA graphs keep theirs). */
+ * environment); returns the previous setting.  Takes effect for subsequent calls (captured CUDA graphs keep theirs).
+ * A pcg_guidance_bwd must run under the setting its pcg_guidance_fwd ran under: the forward keeps only the rows the
+ * backward of the same setting reads. */
 int pcg_set_pooled_last_block(int on);
 /* number of kernels the last fwd / bwd call launched (for bench.py's gpu_launches). */
 int pcg_last_launch_count(void);

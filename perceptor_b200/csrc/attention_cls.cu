@@ -196,6 +196,7 @@ int check_cls(const char* who, int n, int T, int heads, int head_stride) {
     PCG_CHECK_ARG(n > 0 && T > 0 && heads > 0, "%s: bad sizes n=%d T=%d heads=%d", who, n, T, heads);
     PCG_CHECK_ARG(head_stride == 64 || head_stride == 128, "%s: head stride %d is not 64 or 128", who, head_stride);
     PCG_CHECK_ARG(T <= 8192, "%s: T=%d exceeds 8192", who, T);
+    PCG_CHECK_ARG(n <= 65535 && heads <= 65535, "%s: n and heads must be <= 65535 (grid = heads x n)", who);
     return 0;
 }
 
